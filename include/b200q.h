@@ -1,0 +1,180 @@
+/*
+ * b200q.h — C ABI of libb200q.so: the B200 (sm_100a) native kernels for the quantized
+ * hot path of the Wan2.1 DiT denoising loop.
+ *
+ * This is the drop-in boundary that replaces the reference's pybind11 torch-extension
+ * modules `viditq_extension.fused` / `viditq_extension.qgemm`
+ * (ViDiT-Q/kernels/csrc/fused/pybind.cpp:56-99, ViDiT-Q/kernels/csrc/qgemm/pybind.cpp:5-12,
+ * declarations ViDiT-Q/kernels/csrc/qgemm/gemm_cuda.h:17-23) and, above them, the
+ * elementwise torch arithmetic of the fake-quant path
+ * (ViDiT-Q/quant_utils/qdiff/base/base_quantizer.py:58-162, quant_layer.py:57-74).
+ *
+ * Conventions
+ *  - plain pointers and sizes only: every pointer is a DEVICE pointer unless stated,
+ *    every tensor is row-major with an explicit leading dimension in ELEMENTS,
+ *  - the caller allocates all outputs; the library never allocates or frees device memory
+ *    and holds no reference to a caller buffer after the call returns (TMA descriptors are
+ *    built per call on the host stack and passed by value to the kernel),
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), reentrant,
+ *    and performs no host synchronisation,
+ *  - return value: 0 = ok, negative = error (see enum); b200q_last_error() returns a
+ *    thread-local human-readable message for the last failing call on this thread,
+ *  - no shape-divisibility requirements: ragged M/N/K tails are predicated in-kernel
+ *    (the reference asserts M%128, N%128, K%64: w8a8_gemm_cuda.cu:678-680),
+ *  - numerics follow the reference fake-quant path, NOT the reference's fast-math kernels:
+ *    IEEE fp32 division by delta and round-half-to-even (base_quantizer.py:119,155).
+ */
+#ifndef B200Q_H_
+#define B200Q_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum b200q_status {
+  B200Q_OK = 0,
+  B200Q_ERR_BAD_ARG = -1,      /* null pointer, negative size, misaligned pointer, bad enum */
+  B200Q_ERR_UNSUPPORTED = -2,  /* valid request this build cannot serve (e.g. row too long)  */
+  B200Q_ERR_CUDA = -3          /* a CUDA runtime / driver call or the launch failed          */
+};
+
+enum b200q_dtype { B200Q_F32 = 0, B200Q_BF16 = 1, B200Q_F16 = 2, B200Q_I32 = 3 };
+
+/* GEMM epilogues (b200q_gemm_w8a8 / b200q_gemm_w4a8) */
+enum b200q_epilogue {
+  B200Q_EPI_NONE = 0,          /* out = deq(acc) + bias                                              */
+  B200Q_EPI_GELU_TANH = 1,     /* out = gelu_tanh(deq(acc) + bias)          (ffn.0 -> GELU, model.py:286-288) */
+  B200Q_EPI_GATE_RESIDUAL = 2  /* out = residual + (deq(acc)+bias)*gate[n]  (x + y*e, model.py:337,362)        */
+};
+
+typedef void* b200q_stream_t;
+
+#if defined(__GNUC__)
+#define B200Q_API __attribute__((visibility("default")))
+#else
+#define B200Q_API
+#endif
+
+/* ---- library ---------------------------------------------------------------------- */
+B200Q_API int b200q_version(void);                 /* (major<<16)|(minor<<8)|patch */
+B200Q_API const char* b200q_last_error(void);      /* thread-local; "" if none    */
+/* sm count / compute capability of the current device; errors if it is not sm_100. */
+B200Q_API int b200q_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---- (a) per-row quantizer ---------------------------------------------------------
+ * One (delta, zero_point) per row; rows = tokens for activations, out-channels for weights.
+ * Replaces DynamicQuantizer.quantize (base_quantizer.py:110-157), StaticQuantizer.
+ * init_quant_params+quantize (base_quantizer.py:58-99) and the reference kernel
+ * fused.quant_sum (kernels/csrc/fused/fused.cu:30-131, 524-645).
+ *   sym : n_levels = 2^(b-1)-1 ; delta = amax/n_levels ; (dynamic: delta<1e-6 -> 1e-6) ; zp = 0
+ *   asym: n_levels = 2^b ; delta = (max(rowmax,0)-min(rowmin,0))/(n_levels-1) ;
+ *         zp = rne(xmin/delta) + n_levels/2
+ *   q = rne(x/delta) - zp, stored as int8 (saturated to [-128,127]; the reference clamp
+ *   [-n_levels-1, n_levels] never binds).  rowsum[r] = sum_c q[r,c] (int32) feeds the
+ *   zero-point term of the GEMM epilogue.  delta / zero_point / rowsum: [rows]; rowsum may be NULL.
+ *   x_dtype: B200Q_F32 | B200Q_BF16 | B200Q_F16 (up-cast to fp32, arithmetic in fp32).
+ *   stat_max / stat_min (optional, [rows]): the row statistics the parameters were derived from
+ *   (sym: |x| max in stat_max; asym: max(rowmax,0), min(rowmin,0)) = the quantizers' x_absmax /
+ *   x_max / x_min attributes (base_quantizer.py:74-75,81-86,116-117,132-138).
+ */
+B200Q_API int b200q_quant_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                     int n_bits, int sym, int dynamic,
+                     int8_t* q, int64_t ldq, float* delta, float* zero_point, int32_t* rowsum,
+                     float* stat_max, float* stat_min, b200q_stream_t stream);
+
+/* Quantize with precomputed per-row parameters (StaticQuantizer.quantize after init_done,
+ * base_quantizer.py:63-68; reference kernel fused.quant_sum_static). Codes clamp to
+ * [max(-n_levels-1,-128), min(n_levels,127)]. */
+B200Q_API int b200q_quant_rows_static(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                            int n_bits, int sym, const float* delta, const float* zero_point,
+                            int8_t* q, int64_t ldq, int32_t* rowsum, b200q_stream_t stream);
+
+/* out[r,c] = (q[r,c] + zero_point[r]) * delta[r]   (base_quantizer.py:159-162) */
+B200Q_API int b200q_dequant_rows(const int8_t* q, int64_t ldq, int64_t rows, int64_t cols,
+                       const float* delta, const float* zero_point,
+                       void* out, int out_dtype, int64_t ldo, b200q_stream_t stream);
+
+/* ---- (d) calibration reduction -------------------------------------------------------
+ * Single read of x[rows, cols]; running per-channel statistics
+ *   absmax_io[c] = max(absmax_io[c], max_r |x[r,c]|)   (get_calib_data_wanx.py:262-263;
+ *   min_io[c]    = min(min_io[c],    min_r  x[r,c])     merge :443-468 + ptq_wanx.py:336
+ *   max_io[c]    = max(max_io[c],    max_r  x[r,c])     == running elementwise max)
+ * Any of the three may be NULL.  Caller initialises absmax_io to 0, min_io to +inf,
+ * max_io to -inf once; the buffers then accumulate over calls (and over ranks with an
+ * NCCL allreduce(MAX/MIN) on the same buffers).  NaNs are ignored.
+ */
+B200Q_API int b200q_calib_absmax_minmax(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                              float* absmax_io, float* min_io, float* max_io,
+                              b200q_stream_t stream);
+
+/* ---- (b) quantized linear ------------------------------------------------------------
+ * out[m,n] = epi( delta_a[m]*delta_w[n] * ( sum_k qa[m,k]*qw[n,k] + zp_w[n]*rowsum_a[m] ) + bias[n] )
+ * Replaces F.linear on the two dequantised operands (quant_layer.py:70) and the reference
+ * kernels qgemm.w8a8_of16_bias_weight_asym / _sym / w8a8_o32
+ * (kernels/csrc/qgemm/w8a8/w8a8_gemm_cuda.cu:14-838, epilogue :416-441).
+ *   qa [M,K] int8 (lda), qw [N,K] int8 (ldw): both K-major; lda, ldw multiples of 16 and
+ *   base pointers 16-byte aligned (TMA global-stride rule); M, N, K arbitrary (>0).
+ *   delta_a [M], delta_w [N] fp32; zp_w [N] fp32 integers or NULL (symmetric weights);
+ *   rowsum_a [M] int32, required iff zp_w != NULL; bias [N] of bias_dtype or NULL.
+ *   out_dtype B200Q_BF16 | B200Q_F16 | B200Q_F32: dequantised output;
+ *   out_dtype B200Q_I32: raw int32 accumulators (delta/zp/bias/epilogue ignored).
+ *   epilogue B200Q_EPI_GATE_RESIDUAL: residual [M,N] fp32 (ldr), gate [N] fp32;
+ *   `out` may alias `residual` when out_dtype == B200Q_F32 and ldo == ldr.
+ */
+B200Q_API int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw,
+                    const float* delta_a, const float* delta_w, const float* zp_w,
+                    const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                    void* out, int out_dtype, int64_t ldo,
+                    int64_t M, int64_t N, int64_t K,
+                    int epilogue, const float* residual, int64_t ldr, const float* gate,
+                    b200q_stream_t stream);
+
+/* codes int8 [N,K] in [-8,7] -> packed uint8 [N,K/2]: byte j of row n holds code[n,2j] in
+ * bits 0-3 and code[n,2j+1] in bits 4-7 (two's-complement nibbles). K must be even. */
+B200Q_API int b200q_pack_w4(const int8_t* codes, int64_t ld, int64_t N, int64_t K,
+                  uint8_t* packed, int64_t ldp, b200q_stream_t stream);
+
+/* Same contract as b200q_gemm_w8a8 with 4-bit weights packed by b200q_pack_w4
+ * (replaces qgemm.w4a8_of16_nobias_weight_asym_qserve,
+ *  kernels/csrc/qgemm/w4a8/w4a8_per_channel_gemm_cuda_qserve.cu:304-656).
+ * qw4 [N,K/2] uint8 (ldw4 bytes, multiple of 16); nibbles are sign-extended to int8 in
+ * shared memory before the MMA. */
+B200Q_API int b200q_gemm_w4a8(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4,
+                    const float* delta_a, const float* delta_w, const float* zp_w,
+                    const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                    void* out, int out_dtype, int64_t ldo,
+                    int64_t M, int64_t N, int64_t K,
+                    int epilogue, const float* residual, int64_t ldr, const float* gate,
+                    b200q_stream_t stream);
+
+/* ---- fused token-local operators (next-row f-1) ----------------------------------------
+ * LayerNorm (fp32 two-pass statistics, eps) -> optional affine (ln_w, ln_b: [cols] or NULL)
+ * -> optional adaLN modulate  y = ln*(1+scale[c]) + shift[c]  (scale/shift [cols] fp32 or NULL)
+ * -> per-token symmetric n_bits quantisation (same contract as b200q_quant_rows sym dynamic).
+ * Replaces WanLayerNorm + modulation + a_quantizer (wan/modules/model.py:92-102,327,359;
+ * reference kernel fused.layernorm_nobias_t2i_quant_sum_fuse, fused.cu:234-380, 708-915,
+ * which cannot launch for hidden > 4096).  y_out (optional, dtype y_dtype) receives the
+ * un-quantised normalised activations (FP layers / debugging).
+ */
+B200Q_API int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                       const float* ln_w, const float* ln_b, float eps,
+                       const float* shift, const float* scale, int n_bits,
+                       int8_t* q, int64_t ldq, float* delta, int32_t* rowsum,
+                       void* y_out, int y_dtype, int64_t ldy, b200q_stream_t stream);
+
+/* out = residual + y*gate[c]  (fp32 residual stream; y of y_dtype).  Replaces
+ * `x = x + y * e[2]` (model.py:337,362) / reference fused.gate_residual_fuse (fused.cu:382-483).
+ * gate may be NULL (plain residual add, model.py:352). out may alias residual. */
+B200Q_API int b200q_gate_residual(const void* y, int y_dtype, int64_t ldy, const float* gate,
+                        const float* residual, int64_t ldr, float* out, int64_t ldo,
+                        int64_t rows, int64_t cols, b200q_stream_t stream);
+
+/* ---- (c) quantized attention ------------------------------------------------------------
+ * See DESIGN.md §attention; declared in later sections of this header as they land. */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200Q_H_ */

@@ -1,0 +1,144 @@
+"""-m gpu parity tests: tcgen05 int8 GEMM through the C ABI.  int32 accumulators BIT-EXACT vs the oracle;
+dequantised outputs within the stated tolerance (cosine >= 0.999, max rel err stated per test)."""
+import os
+
+import pytest
+import torch
+
+import b200q
+from oracle import fakequant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _codes(rows, cols, seed, lo=-127, hi=127):
+    g = torch.Generator().manual_seed(seed)
+    return torch.randint(lo, hi + 1, (rows, cols), generator=g, dtype=torch.int32).to(torch.int8)
+
+
+SHAPES = [(128, 256, 128), (256, 512, 256), (384, 256, 1536), (130, 270, 144), (1, 8, 16), (515, 1536, 1536),
+          (100, 100, 4096), (128, 8960, 320), (777, 300, 208)]
+
+
+@pytest.mark.parametrize("M,N,K", SHAPES)
+def test_int32_accumulators_bit_exact(dev, M, N, K):
+    qa, qw = _codes(M, K, M + K), _codes(N, K, N + K + 1, -128, 127)
+    acc = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), out_dtype=torch.int32)
+    assert torch.equal(acc.cpu(), O.int_accumulators(qa, qw))
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+@pytest.mark.parametrize("out_dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 8e-3), (torch.float16, 1e-3)])
+@pytest.mark.parametrize("M,N,K", [(300, 520, 1536), (64, 256, 8960), (129, 40, 136)])
+def test_dequant_epilogue(dev, M, N, K, out_dtype, tol):
+    """Distribution of ViDiT-Q/kernels/bench/bench_gemm.py:4-16 (codes in [-80,80), positive scales, zp in [-10,10))."""
+    g = torch.Generator().manual_seed(M * 3 + N)
+    qa, qw = _codes(M, K, 1, -80, 79), _codes(N, K, 2, -80, 79)
+    da = torch.rand(M, generator=g) * 0.01 + 0.005
+    dw = torch.rand(N, generator=g) * 0.1 + 0.1
+    zp = torch.randint(-10, 10, (N,), generator=g).float()
+    bias = torch.rand(N, generator=g) * 200
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+    acc = O.int_accumulators(qa, qw).double()
+    ref = (da.double()[:, None] * dw.double()[None, :] * (acc + zp.double()[None, :] * rs.double()[:, None])
+           + bias.double()[None, :])
+    out = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), da.to(dev), dw.to(dev), zp.to(dev), rs.to(dev), bias.to(dev),
+                          out_dtype=out_dtype)
+    got = out.cpu().double()
+    rel = float(((got - ref).abs() / (ref.abs() + 1.0)).max())
+    assert rel <= tol, rel
+    assert _cos(got, ref) >= 0.99999
+    # symmetric weights, no bias
+    out = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), da.to(dev), dw.to(dev), out_dtype=out_dtype)
+    ref2 = da.double()[:, None] * dw.double()[None, :] * acc
+    rel = float(((out.cpu().double() - ref2).abs() / (ref2.abs() + 1.0)).max())
+    assert rel <= tol, rel
+
+
+@pytest.mark.parametrize("name", ["w8a8"])
+def test_quantized_linear_golden(dev, golden_dir, name):
+    """End to end vs the imported reference's QuantizedLinear.forward (quant_layer.py:57-74): quantizer kernels +
+    GEMM kernel reproduce its fp32 fake-quant output.  Tolerance: max |err| <= 2e-5 * (|y| + 1) in fp32."""
+    rec = torch.load(os.path.join(golden_dir, "quantized_linear.pt"))[name]
+    x = rec["x"].reshape(-1, rec["x"].shape[-1]).to(dev)
+    qw, dw, zw, _ = b200q.quant_rows(rec["weight"].to(dev), rec["w_bits"], False, False, want_rowsum=False)
+    assert torch.equal(dw.cpu(), rec["w_delta"].flatten()) and torch.equal(zw.cpu(), rec["w_zero_point"].flatten())
+    qa, da, _, rs = b200q.quant_rows(x, 8, True, True)
+    assert torch.equal(da.cpu(), rec["a_delta"].flatten())
+    K = x.shape[1]
+    Kp = (K + 15) // 16 * 16                                   # TMA needs 16-byte row pitch: pad K with zero codes
+    qa_p = torch.zeros(qa.shape[0], Kp, dtype=torch.int8, device=dev); qa_p[:, :K] = qa
+    qw_p = torch.zeros(qw.shape[0], Kp, dtype=torch.int8, device=dev); qw_p[:, :K] = qw
+    y = b200q.gemm_w8a8(qa_p[:, :K], qw_p[:, :K], da, dw, zw, rs, rec["bias"].to(dev), out_dtype=torch.float32)
+    ref = rec["y"].reshape(-1, rec["y"].shape[-1])
+    err = (y.cpu() - ref).abs() / (ref.abs() + 1.0)
+    assert float(err.max()) <= 2e-5, float(err.max())
+    assert _cos(y.cpu(), ref) >= 0.999999
+
+
+def test_gelu_epilogue(dev):
+    M, N, K = 200, 512, 256
+    g = torch.Generator().manual_seed(9)
+    qa, qw = _codes(M, K, 3), _codes(N, K, 4)
+    da = torch.rand(M, generator=g) * 2e-4 + 1e-5
+    dw = torch.rand(N, generator=g) * 1e-2 + 1e-3
+    bias = torch.randn(N, generator=g) * 0.1
+    pre = da[:, None].double() * dw[None, :].double() * O.int_accumulators(qa, qw).double() + bias.double()
+    ref = torch.nn.functional.gelu(pre.float(), approximate="tanh")
+    out = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), da.to(dev), dw.to(dev), None, None, bias.to(dev),
+                          out_dtype=torch.float32, epilogue=b200q.EPI_GELU_TANH)
+    assert float((out.cpu() - ref).abs().max()) <= 2e-3 * float(ref.abs().max() + 1)   # tanh.approx.f32: ~2^-11 rel
+    assert _cos(out.cpu(), ref) >= 0.99999
+
+
+def test_gate_residual_epilogue(dev):
+    M, N, K = 333, 768, 512
+    g = torch.Generator().manual_seed(10)
+    qa, qw = _codes(M, K, 5), _codes(N, K, 6)
+    da = torch.rand(M, generator=g) * 2e-4 + 1e-5
+    dw = torch.rand(N, generator=g) * 1e-2 + 1e-3
+    zp = torch.randint(-3, 4, (N,), generator=g).float()
+    bias = torch.randn(N, generator=g) * 0.1
+    gate = torch.randn(N, generator=g)
+    res = torch.randn(M, N, generator=g)
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+    acc = O.int_accumulators(qa, qw).double() + zp.double()[None, :] * rs.double()[:, None]
+    y = da[:, None].double() * dw[None, :].double() * acc + bias.double()
+    ref = res.double() + y * gate.double()
+    x = res.clone().to(dev)
+    out = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), da.to(dev), dw.to(dev), zp.to(dev), rs.to(dev), bias.to(dev),
+                          epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=gate.to(dev))
+    assert out.data_ptr() == x.data_ptr()
+    assert float((out.cpu().double() - ref).abs().max()) <= 1e-4
+
+
+def test_full_size_linearity_and_checksum(dev):
+    """BASELINE config 1 shape (32760 x 1536 x 1536): properties instead of a CPU recomputation —
+    column checksum of the accumulators equals (sum_m qa) @ qw^T computed in int64 on a reduced problem,
+    and acc(qa1 + qa2) == acc(qa1) + acc(qa2)."""
+    L, D = 32760, 1536
+    qa1 = torch.randint(-60, 61, (L, D), device=dev, dtype=torch.int8)
+    qa2 = torch.randint(-60, 61, (L, D), device=dev, dtype=torch.int8)
+    qw = torch.randint(-128, 128, (D, D), device=dev, dtype=torch.int8)
+    a1 = b200q.gemm_w8a8(qa1, qw, out_dtype=torch.int32)
+    a2 = b200q.gemm_w8a8(qa2, qw, out_dtype=torch.int32)
+    a12 = b200q.gemm_w8a8(qa1 + qa2, qw, out_dtype=torch.int32)
+    assert torch.equal(a12, a1 + a2)
+    colsum = a1.sum(dim=0, dtype=torch.int64)
+    ref = (qa1.sum(dim=0, dtype=torch.int64).double()[None, :] @ qw.double().t()).flatten()
+    assert torch.equal(colsum.double(), ref)
+    idx = torch.randint(0, L, (48,), device=dev)
+    assert torch.equal(a1[idx].cpu(), O.int_accumulators(qa1[idx].cpu(), qw.cpu()))
+
+
+def test_bad_arguments_raise(dev):
+    qa = torch.zeros(8, 24, dtype=torch.int8, device=dev)      # lda = 24 is not a multiple of 16
+    qw = torch.zeros(8, 24, dtype=torch.int8, device=dev)
+    with pytest.raises(b200q.B200QError):
+        b200q.gemm_w8a8(qa, qw, out_dtype=torch.int32)
+    with pytest.raises(b200q.B200QError):
+        b200q.quant_rows(torch.zeros(4, 4), 8, True, True)     # CPU tensor: no fallback

@@ -1,0 +1,293 @@
+"""b200q — ctypes binding of libb200q.so (C ABI in include/b200q.h).
+
+PyTorch here is plumbing only: it owns device memory and streams; every op below hands raw
+`data_ptr()`s, sizes and the current CUDA stream to the hand-written sm_100a kernels.
+There is NO CPU / eager fallback: a missing library or a non-CUDA tensor raises.
+
+Mirrors what the reference reaches through `viditq_extension.{fused,qgemm}`
+(ViDiT-Q/kernels/csrc/fused/pybind.cpp:56-99, kernels/csrc/qgemm/pybind.cpp:5-12).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_void_p
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "lib", "libb200q.so")
+
+F32, BF16, F16, I32 = 0, 1, 2, 3
+EPI_NONE, EPI_GELU_TANH, EPI_GATE_RESIDUAL = 0, 1, 2
+
+_DTYPE = {torch.float32: F32, torch.bfloat16: BF16, torch.float16: F16, torch.int32: I32}
+
+_lib = None
+# incremented on every successful kernel-launching call (bench.py reports it as gpu_launches)
+launch_count = 0
+
+
+class B200QError(RuntimeError):
+    pass
+
+
+_SIGNATURES = {
+    "b200q_version": (c_int, []),
+    "b200q_last_error": (c_char_p, []),
+    "b200q_device_info": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "b200q_quant_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int, c_int,
+                                 c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200q_quant_rows_static": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_int,
+                                        c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200q_dequant_rows": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int64, c_void_p]),
+    "b200q_calib_absmax_minmax": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64,
+                                          c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200q_gemm_w8a8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200q_gemm_w4a8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
+                                c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200q_pack_w4": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
+    "b200q_ln_mod_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
+                                   c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
+                                   c_void_p, c_int, c_int64, c_void_p]),
+    "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
+                                    c_int64, c_int64, c_void_p]),
+}
+
+
+def exported_symbols():
+    """Names every build of the library must export (tests compare with include/b200q.h)."""
+    return sorted(_SIGNATURES)
+
+
+def load():
+    """dlopen the library once; fail loudly when it was not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise B200QError(
+            f"{LIB_PATH} not found: build it with `python wan2.1-quantization_b200/build.py` "
+            "(there is no CPU fallback for the quantized hot path)")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in _SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError if the build lacks a declared symbol
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def version():
+    v = load().b200q_version()
+    return (v >> 16, (v >> 8) & 0xFF, v & 0xFF)
+
+
+def _check(rc, what):
+    global launch_count
+    if rc != 0:
+        msg = load().b200q_last_error().decode("utf-8", "replace")
+        raise B200QError(f"{what} failed (status {rc}): {msg}")
+    launch_count += 1
+
+
+def _cuda(t: torch.Tensor, name: str):
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise B200QError(f"{name}: expected a CUDA tensor — libb200q has no CPU path")
+    return t
+
+
+def _stream():
+    return c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def _rows2d(x, name):
+    _cuda(x, name)
+    if x.dim() != 2:
+        raise B200QError(f"{name}: expected a 2-D [rows, cols] tensor, got {tuple(x.shape)}")
+    if x.stride(1) != 1 and x.shape[1] > 1:
+        x = x.contiguous()
+    return x
+
+
+def _ld(x):
+    """leading dimension (elements) of a 2-D row-major view"""
+    return x.stride(0) if x.shape[0] > 1 else max(int(x.shape[1]), 1)
+
+
+# ---------------------------------------------------------------------------------------------
+# (a) per-row quantizer
+# ---------------------------------------------------------------------------------------------
+def quant_rows(x, n_bits=8, sym=True, dynamic=True, want_rowsum=True, out=None, want_stats=False):
+    """x [rows, cols] (fp32|bf16|fp16) -> (codes int8 [rows, cols], delta f32 [rows], zero_point f32 [rows],
+    rowsum int32 [rows] | None).  base_quantizer.py:58-99 (dynamic=False) / :110-157 (dynamic=True).
+    want_stats=True appends (stat_max, stat_min): sym -> (absmax, None); asym -> (max(rowmax,0), min(rowmin,0))."""
+    x = _rows2d(x, "quant_rows")
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise B200QError(f"quant_rows: unsupported dtype {x.dtype}")
+    rows, cols = x.shape
+    q = out if out is not None else torch.empty((rows, cols), dtype=torch.int8, device=x.device)
+    delta = torch.empty(rows, dtype=torch.float32, device=x.device)
+    zp = torch.empty(rows, dtype=torch.float32, device=x.device)
+    rs = torch.empty(rows, dtype=torch.int32, device=x.device) if want_rowsum else None
+    smax = torch.empty(rows, dtype=torch.float32, device=x.device) if want_stats else None
+    smin = torch.empty(rows, dtype=torch.float32, device=x.device) if (want_stats and not sym) else None
+    rc = load().b200q_quant_rows(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), int(n_bits), int(bool(sym)),
+                                 int(bool(dynamic)), _ptr(q), _ld(q), _ptr(delta), _ptr(zp), _ptr(rs),
+                                 _ptr(smax), _ptr(smin), _stream())
+    _check(rc, "b200q_quant_rows")
+    if want_stats:
+        return q, delta, zp, rs, smax, smin
+    return q, delta, zp, rs
+
+
+def quant_rows_static(x, delta, zero_point, n_bits=8, sym=False, want_rowsum=False):
+    """Quantize with given per-row parameters (base_quantizer.py:63-68)."""
+    x = _rows2d(x, "quant_rows_static")
+    rows, cols = x.shape
+    delta = _cuda(delta, "delta").reshape(-1).float().contiguous()
+    zero_point = _cuda(zero_point, "zero_point").reshape(-1).float().contiguous()
+    if delta.numel() != rows or zero_point.numel() != rows:
+        raise B200QError("quant_rows_static: delta / zero_point must have one entry per row")
+    q = torch.empty((rows, cols), dtype=torch.int8, device=x.device)
+    rs = torch.empty(rows, dtype=torch.int32, device=x.device) if want_rowsum else None
+    rc = load().b200q_quant_rows_static(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), int(n_bits), int(bool(sym)),
+                                        _ptr(delta), _ptr(zero_point), _ptr(q), _ld(q), _ptr(rs), _stream())
+    _check(rc, "b200q_quant_rows_static")
+    return q, rs
+
+
+def dequant_rows(q, delta, zero_point=None, out_dtype=torch.float32):
+    """(q + zero_point) * delta  (base_quantizer.py:159-162)."""
+    q = _rows2d(q, "dequant_rows")
+    rows, cols = q.shape
+    delta = _cuda(delta, "delta").reshape(-1).float().contiguous()
+    zp = None if zero_point is None else _cuda(zero_point, "zero_point").reshape(-1).float().contiguous()
+    out = torch.empty((rows, cols), dtype=out_dtype, device=q.device)
+    rc = load().b200q_dequant_rows(_ptr(q), _ld(q), rows, cols, _ptr(delta), _ptr(zp), _ptr(out), _DTYPE[out_dtype],
+                                   _ld(out), _stream())
+    _check(rc, "b200q_dequant_rows")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (d) calibration reduction
+# ---------------------------------------------------------------------------------------------
+def calib_update(x, absmax=None, xmin=None, xmax=None):
+    """Running per-channel |x| max / min / max over the rows of x [rows, cols], in place
+    (get_calib_data_wanx.py:262-263 + the merge :443-468 / ptq_wanx.py:336)."""
+    x = _rows2d(x, "calib_update")
+    rows, cols = x.shape
+    for t in (absmax, xmin, xmax):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or t.numel() != cols or not t.is_contiguous()):
+            raise B200QError("calib_update: statistics buffers must be contiguous fp32 CUDA tensors of [cols]")
+    rc = load().b200q_calib_absmax_minmax(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(absmax), _ptr(xmin),
+                                          _ptr(xmax), _stream())
+    _check(rc, "b200q_calib_absmax_minmax")
+    return absmax, xmin, xmax
+
+
+# ---------------------------------------------------------------------------------------------
+# (b) quantized linear
+# ---------------------------------------------------------------------------------------------
+def _gemm(fn_name, qa, qw, N, K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype, epilogue, residual, gate, out):
+    _cuda(qa, "qa"); _cuda(qw, "qw")
+    M = qa.shape[0]
+    if out is None:
+        if epilogue == EPI_GATE_RESIDUAL:
+            out = residual
+        else:
+            out = torch.empty((M, N), dtype=out_dtype, device=qa.device)
+    bias_dt = _DTYPE[bias.dtype] if bias is not None else F32
+    fn = getattr(load(), fn_name)
+    rc = fn(_ptr(qa), _ld(qa), _ptr(qw), _ld(qw), _ptr(delta_a), _ptr(delta_w), _ptr(zp_w), _ptr(rowsum_a),
+            _ptr(bias), bias_dt, _ptr(out), _DTYPE[out.dtype], _ld(out), M, N, K, int(epilogue),
+            _ptr(residual), _ld(residual) if residual is not None else 0, _ptr(gate), _stream())
+    _check(rc, fn_name)
+    return out
+
+
+def gemm_w8a8(qa, qw, delta_a=None, delta_w=None, zp_w=None, rowsum_a=None, bias=None,
+              out_dtype=torch.bfloat16, epilogue=EPI_NONE, residual=None, gate=None, out=None):
+    """out[m,n] = epi(da[m]*dw[n]*(sum_k qa[m,k]*qw[n,k] + zp_w[n]*rowsum_a[m]) + bias[n]).
+    qa int8 [M,K], qw int8 [N,K].  out_dtype torch.int32 -> raw accumulators."""
+    K = qa.shape[1]
+    if qw.shape[1] != K:
+        raise B200QError(f"gemm_w8a8: K mismatch {qa.shape} vs {qw.shape}")
+    return _gemm("b200q_gemm_w8a8", qa, qw, qw.shape[0], K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype,
+                 epilogue, residual, gate, out)
+
+
+def pack_w4(codes):
+    """int8 codes in [-8,7], [N,K] -> packed uint8 [N, ceil(K/8)*4] (format: csrc/w4.cu)."""
+    codes = _rows2d(codes, "pack_w4")
+    N, K = codes.shape
+    packed = torch.empty((N, ((K + 7) // 8) * 4), dtype=torch.uint8, device=codes.device)
+    rc = load().b200q_pack_w4(_ptr(codes), _ld(codes), N, K, _ptr(packed), _ld(packed), _stream())
+    _check(rc, "b200q_pack_w4")
+    return packed
+
+
+def gemm_w4a8(qa, qw4, K, delta_a=None, delta_w=None, zp_w=None, rowsum_a=None, bias=None,
+              out_dtype=torch.bfloat16, epilogue=EPI_NONE, residual=None, gate=None, out=None):
+    """Same contract as gemm_w8a8 with weights packed by pack_w4 (rowsum_a is always required:
+    the unsigned-nibble bias is folded through the zero-point term)."""
+    return _gemm("b200q_gemm_w4a8", qa, qw4, qw4.shape[0], K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype,
+                 epilogue, residual, gate, out)
+
+
+# ---------------------------------------------------------------------------------------------
+# fused token-local ops
+# ---------------------------------------------------------------------------------------------
+def ln_mod_quant(x, eps, ln_w=None, ln_b=None, shift=None, scale=None, n_bits=8, quant=True,
+                 want_rowsum=True, y_dtype=None):
+    """LayerNorm -> affine -> adaLN modulate -> per-token sym quant.  Returns (q, delta, rowsum, y)."""
+    x = _rows2d(x, "ln_mod_quant")
+    rows, cols = x.shape
+    dev = x.device
+    q = torch.empty((rows, cols), dtype=torch.int8, device=dev) if quant else None
+    delta = torch.empty(rows, dtype=torch.float32, device=dev) if quant else None
+    rs = torch.empty(rows, dtype=torch.int32, device=dev) if (quant and want_rowsum) else None
+    y = torch.empty((rows, cols), dtype=y_dtype, device=dev) if y_dtype is not None else None
+
+    def vec(t, name):
+        if t is None:
+            return None
+        t = _cuda(t, name).reshape(-1)
+        if t.dtype != torch.float32 or t.numel() != cols or not t.is_contiguous():
+            t = t.float().contiguous()
+        if t.numel() != cols:
+            raise B200QError(f"ln_mod_quant: {name} must have {cols} entries")
+        return t
+
+    ln_w, ln_b, shift, scale = vec(ln_w, "ln_w"), vec(ln_b, "ln_b"), vec(shift, "shift"), vec(scale, "scale")
+    rc = load().b200q_ln_mod_quant(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(ln_w), _ptr(ln_b), float(eps),
+                                   _ptr(shift), _ptr(scale), int(n_bits), _ptr(q), _ld(q) if q is not None else 0,
+                                   _ptr(delta), _ptr(rs), _ptr(y), _DTYPE[y_dtype] if y is not None else F32,
+                                   _ld(y) if y is not None else 0, _stream())
+    _check(rc, "b200q_ln_mod_quant")
+    return q, delta, rs, y
+
+
+def gate_residual(y, residual, gate=None, out=None):
+    """out = residual + y*gate (fp32 residual stream; in place on `residual` by default)."""
+    y = _rows2d(y, "gate_residual")
+    residual = _rows2d(residual, "gate_residual")
+    if residual.dtype != torch.float32:
+        raise B200QError("gate_residual: the residual stream is fp32")
+    rows, cols = y.shape
+    out = residual if out is None else out
+    if gate is not None:
+        gate = _cuda(gate, "gate").reshape(-1).float().contiguous()
+    rc = load().b200q_gate_residual(_ptr(y), _DTYPE[y.dtype], _ld(y), _ptr(gate), _ptr(residual), _ld(residual),
+                                    _ptr(out), _ld(out), rows, cols, _stream())
+    _check(rc, "b200q_gate_residual")
+    return out

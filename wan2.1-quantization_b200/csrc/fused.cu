@@ -1,0 +1,311 @@
+// Token-local fused operators around the quantized linears.
+//
+//  b200q_ln_mod_quant : WanLayerNorm (fp32 statistics, wan/modules/model.py:92-102) -> optional affine
+//                       (norm3) -> adaLN modulate `ln*(1+scale)+shift` (model.py:327,359) -> per-token
+//                       symmetric quantizer (base_quantizer.py:110-157).  One HBM read of the fp32
+//                       residual stream, one int8 write; any hidden size up to 32K channels (the reference
+//                       kernel LayernormT2iQuantFuse, kernels/csrc/fused/fused.cu:234-380, needs
+//                       hidden/4 threads and cannot launch for hidden > 4096).
+//  b200q_gate_residual: out = residual + y*gate (model.py:337,362; reference fused.cu:382-483).
+#include "common.cuh"
+
+namespace b200q {
+
+struct LnArgs {
+  const void* x;
+  int64_t rows, cols, ldx;
+  const float* ln_w;
+  const float* ln_b;
+  float eps;
+  const float* shift;
+  const float* scale;
+  float n_levels;
+  int8_t* q;
+  int64_t ldq;
+  float* delta;
+  int32_t* rowsum;
+  void* y_out;
+  int64_t ldy;
+};
+
+__device__ __forceinline__ uint32_t pack4i(int c0, int c1, int c2, int c3) {
+  uint32_t t0 = __byte_perm((uint32_t)c0, (uint32_t)c1, 0x0040);
+  uint32_t t1 = __byte_perm((uint32_t)c2, (uint32_t)c3, 0x0040);
+  return __byte_perm(t0, t1, 0x5410);
+}
+
+// cross-warp (within one row's warps) reductions through shared memory
+__device__ __forceinline__ float row_reduce_sum(float v, float* s_buf, int warp, int lane, int w0, int wpr) {
+  v = warp_sum(v);
+  if (wpr > 1) {
+    __syncthreads();                      // protect s_buf reuse
+    if (lane == 0) s_buf[warp] = v;
+    __syncthreads();
+    v = warp_sum(lane < wpr ? s_buf[w0 + lane] : 0.f);
+  }
+  return v;
+}
+__device__ __forceinline__ float row_reduce_max(float v, float* s_buf, int warp, int lane, int w0, int wpr) {
+  v = warp_max(v);
+  if (wpr > 1) {
+    __syncthreads();
+    if (lane == 0) s_buf[warp] = v;
+    __syncthreads();
+    v = warp_max(lane < wpr ? s_buf[w0 + lane] : 0.f);
+  }
+  return v;
+}
+
+template <typename T, typename YT, int V, int THREADS>
+__global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, const int warps_per_row) {
+  using VT = Vec16<T>;
+  constexpr int N = VT::N;
+  __shared__ float s_buf[32];
+  __shared__ int s_sum[32];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_cta = (blockDim.x >> 5) / warps_per_row;
+  const int row_in_cta = warp / warps_per_row;
+  const int w0 = row_in_cta * warps_per_row;
+  const int wr = warp - w0;
+  const int64_t row = (int64_t)blockIdx.x * rows_per_cta + row_in_cta;
+  const bool row_ok = row < a.rows;
+  const int tpr = warps_per_row * 32;
+  const int t = wr * 32 + lane;
+  const int kv = (int)(a.cols / N);
+  const float inv_c = 1.f / (float)a.cols;
+
+  const T* xrow = reinterpret_cast<const T*>(a.x) + (row_ok ? row : 0) * a.ldx;
+  float f[V][N];
+  float s = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int j = v * tpr + t;
+    const uint4 raw = (row_ok && j < kv) ? ldg_stream16(xrow + (int64_t)j * N) : make_uint4(0, 0, 0, 0);
+    VT::unpack(raw, f[v]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) s += f[v][i];
+  }
+  const float mean = row_reduce_sum(s, s_buf, warp, lane, w0, warps_per_row) * inv_c;
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const bool live = (v * tpr + t) < kv;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float d = f[v][i] - mean;
+      ss += live ? d * d : 0.f;
+    }
+  }
+  const float var = row_reduce_sum(ss, s_buf, warp, lane, w0, warps_per_row) * inv_c;
+  const float rstd = __frsqrt_rn(var + a.eps);
+
+  float amax = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int j = v * tpr + t;
+    const bool live = j < kv;
+    const int c0 = j * N;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      float y = (f[v][i] - mean) * rstd;
+      if (live) {
+        if (a.ln_w) y = __fmul_rn(y, a.ln_w[c0 + i]);
+        if (a.ln_b) y = __fadd_rn(y, a.ln_b[c0 + i]);
+        if (a.scale) y = __fmul_rn(y, __fadd_rn(1.f, a.scale[c0 + i]));   // ln*(1+e1)   model.py:327
+        if (a.shift) y = __fadd_rn(y, a.shift[c0 + i]);                   //  + e0
+      } else {
+        y = 0.f;
+      }
+      f[v][i] = y;
+      amax = fmaxf(amax, fabsf(y));
+    }
+    if (a.y_out != nullptr && row_ok && live) {
+      YT* yrow = reinterpret_cast<YT*>(a.y_out) + row * a.ldy + c0;
+#pragma unroll
+      for (int i = 0; i < N; ++i) yrow[i] = from_f32<YT>(f[v][i]);
+    }
+  }
+  if (a.q == nullptr) return;       // uniform across the CTA
+
+  amax = row_reduce_max(amax, s_buf, warp, lane, w0, warps_per_row);
+  float delta = __fdiv_rn(amax, a.n_levels);
+  if (delta < 1.0e-6f) delta = 1.0e-6f;                                   // base_quantizer.py:122-128
+  const float r = __frcp_rn(delta);
+  int8_t* qrow = a.q + (row_ok ? row : 0) * a.ldq;
+  int sum = 0;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int j = v * tpr + t;
+    uint32_t packed[N / 4];
+#pragma unroll
+    for (int g = 0; g < N / 4; ++g) {
+      int c[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) c[i] = rne_to_int_bits(div_rn_hoisted(f[v][4 * g + i], delta, r));
+      packed[g] = pack4i(c[0], c[1], c[2], c[3]);
+      sum = __dp4a((int)packed[g], 0x01010101, sum);
+    }
+    if (row_ok && j < kv) {
+      if (N == 4) stg_stream4(qrow + (int64_t)j * N, packed[0]);
+      else stg_stream8(qrow + (int64_t)j * N, make_uint2(packed[0], packed[N / 4 - 1]));
+    }
+  }
+  if (a.rowsum != nullptr) {
+    sum = warp_sum(sum);
+    if (warps_per_row > 1) {
+      __syncthreads();
+      if (lane == 0) s_sum[warp] = sum;
+      __syncthreads();
+      sum = warp_sum(lane < warps_per_row ? s_sum[w0 + lane] : 0);
+    }
+    if (row_ok && t == 0) a.rowsum[row] = sum;
+  }
+  if (row_ok && t == 0) a.delta[row] = delta;
+}
+
+template <typename T, typename YT>
+static int launch_ln(const LnArgs& a, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  const int kv = (int)(a.cols / N);
+  int W = 1;
+  while (W < 8 && (kv + 32 * W - 1) / (32 * W) > 4) W *= 2;
+  int threads = 256;
+  if ((kv + 32 * W - 1) / (32 * W) > 8) { W = 32; threads = 1024; }
+  const int V = (kv + 32 * W - 1) / (32 * W);
+  B200Q_REQUIRE(V <= 8, B200Q_ERR_UNSUPPORTED, "ln_mod_quant: cols=%lld too large (max %d)", (long long)a.cols, 8 * 1024 * N);
+  const int rows_per_cta = (threads / 32) / W;
+  const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
+#define B200Q_LN(VV, TH) ln_mod_quant_kernel<T, YT, VV, TH><<<grid, TH, 0, st>>>(a, W)
+  if (threads == 1024) { if (V <= 4) B200Q_LN(4, 1024); else B200Q_LN(8, 1024); }
+  else if (V <= 1) B200Q_LN(1, 256);
+  else if (V <= 2) B200Q_LN(2, 256);
+  else if (V <= 3) B200Q_LN(3, 256);
+  else if (V <= 4) B200Q_LN(4, 256);
+  else if (V <= 6) B200Q_LN(6, 256);
+  else B200Q_LN(8, 256);
+#undef B200Q_LN
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
+// ---- gate residual ---------------------------------------------------------------------------------------
+template <typename YT>
+__global__ void __launch_bounds__(256) gate_residual_kernel(const YT* __restrict__ y, int64_t ldy,
+                                                             const float* __restrict__ gate,
+                                                             const float* residual, int64_t ldr, float* out,
+                                                             int64_t ldo, int64_t rows, int64_t cols4) {
+  const int64_t total = rows * cols4;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols4, c = (i - r * cols4) * 4;
+    float yv[4];
+    if constexpr (sizeof(YT) == 4) {
+      const float4 t = *reinterpret_cast<const float4*>(y + r * ldy + c);
+      yv[0] = t.x; yv[1] = t.y; yv[2] = t.z; yv[3] = t.w;
+    } else {
+      const uint2 t = *reinterpret_cast<const uint2*>(y + r * ldy + c);
+      const YT* h = reinterpret_cast<const YT*>(&t);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) yv[k] = to_f32(h[k]);
+    }
+    const float4 res = *reinterpret_cast<const float4*>(residual + r * ldr + c);
+    float4 g = make_float4(1.f, 1.f, 1.f, 1.f);
+    if (gate) g = *reinterpret_cast<const float4*>(gate + c);
+    float4 o;
+    // x + y*e : two roundings like the reference's separate mul and add (model.py:337)
+    o.x = __fadd_rn(res.x, __fmul_rn(yv[0], g.x));
+    o.y = __fadd_rn(res.y, __fmul_rn(yv[1], g.y));
+    o.z = __fadd_rn(res.z, __fmul_rn(yv[2], g.z));
+    o.w = __fadd_rn(res.w, __fmul_rn(yv[3], g.w));
+    *reinterpret_cast<float4*>(out + r * ldo + c) = o;
+  }
+}
+
+template <typename YT>
+__global__ void __launch_bounds__(256) gate_residual_scalar_kernel(const YT* __restrict__ y, int64_t ldy,
+                                                                    const float* __restrict__ gate,
+                                                                    const float* residual, int64_t ldr, float* out,
+                                                                    int64_t ldo, int64_t rows, int64_t cols) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    const float g = gate ? gate[c] : 1.f;
+    out[r * ldo + c] = __fadd_rn(residual[r * ldr + c], __fmul_rn(to_f32(y[r * ldy + c]), g));
+  }
+}
+
+template <typename YT>
+static int launch_gate(const void* y, int64_t ldy, const float* gate, const float* residual, int64_t ldr, float* out,
+                       int64_t ldo, int64_t rows, int64_t cols, cudaStream_t st) {
+  const YT* yp = reinterpret_cast<const YT*>(y);
+  const bool vec = cols % 4 == 0 && ldy % 4 == 0 && ldr % 4 == 0 && ldo % 4 == 0 && aligned(y, 4 * sizeof(YT)) &&
+                   aligned(residual, 16) && aligned(out, 16) && (!gate || aligned(gate, 16));
+  const int64_t work = vec ? rows * (cols / 4) : rows * cols;
+  int64_t blocks = (work + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 32;
+  if (blocks > cap) blocks = cap;
+  if (vec) gate_residual_kernel<YT><<<(unsigned)blocks, 256, 0, st>>>(yp, ldy, gate, residual, ldr, out, ldo, rows, cols / 4);
+  else gate_residual_scalar_kernel<YT><<<(unsigned)blocks, 256, 0, st>>>(yp, ldy, gate, residual, ldr, out, ldo, rows, cols);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                                  const float* ln_w, const float* ln_b, float eps, const float* shift,
+                                  const float* scale, int n_bits, int8_t* q, int64_t ldq, float* delta,
+                                  int32_t* rowsum, void* y_out, int y_dtype, int64_t ldy, b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "ln_mod_quant: negative shape");
+  if (rows == 0 || cols == 0) return B200Q_OK;
+  B200Q_REQUIRE(x != nullptr && (q != nullptr || y_out != nullptr), B200Q_ERR_BAD_ARG, "ln_mod_quant: null pointer");
+  B200Q_REQUIRE(q == nullptr || delta != nullptr, B200Q_ERR_BAD_ARG, "ln_mod_quant: delta required with q");
+  B200Q_REQUIRE(n_bits >= 2 && n_bits <= 8, B200Q_ERR_BAD_ARG, "ln_mod_quant: n_bits=%d out of [2,8]", n_bits);
+  B200Q_REQUIRE(ldx >= cols && (q == nullptr || ldq >= cols) && (y_out == nullptr || ldy >= cols), B200Q_ERR_BAD_ARG,
+                "ln_mod_quant: leading dimension < cols");
+  const int vecn = x_dtype == B200Q_F32 ? 4 : 8;
+  B200Q_REQUIRE(cols % vecn == 0 && ldx % vecn == 0 && aligned(x, 16), B200Q_ERR_UNSUPPORTED,
+                "ln_mod_quant: cols and ldx must be multiples of %d and x 16-byte aligned", vecn);
+  B200Q_REQUIRE(q == nullptr || (ldq % vecn == 0 && aligned(q, vecn)), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: q misaligned");
+  LnArgs a{};
+  a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps;
+  a.shift = shift; a.scale = scale; a.n_levels = (float)((1 << (n_bits - 1)) - 1);
+  a.q = q; a.ldq = ldq; a.delta = delta; a.rowsum = rowsum; a.y_out = y_out; a.ldy = ldy;
+  cudaStream_t st = (cudaStream_t)stream;
+#define B200Q_LN_Y(T)                                                                  \
+  switch (y_out ? y_dtype : B200Q_F32) {                                               \
+    case B200Q_F32: return launch_ln<T, float>(a, st);                                 \
+    case B200Q_BF16: return launch_ln<T, __nv_bfloat16>(a, st);                        \
+    case B200Q_F16: return launch_ln<T, __half>(a, st);                                \
+    default: set_error("ln_mod_quant: bad y_dtype %d", y_dtype); return B200Q_ERR_BAD_ARG; \
+  }
+  switch (x_dtype) {
+    case B200Q_F32: B200Q_LN_Y(float)
+    case B200Q_BF16: B200Q_LN_Y(__nv_bfloat16)
+    case B200Q_F16: B200Q_LN_Y(__half)
+  }
+#undef B200Q_LN_Y
+  set_error("ln_mod_quant: bad x_dtype %d", x_dtype);
+  return B200Q_ERR_BAD_ARG;
+}
+
+extern "C" int b200q_gate_residual(const void* y, int y_dtype, int64_t ldy, const float* gate, const float* residual,
+                                   int64_t ldr, float* out, int64_t ldo, int64_t rows, int64_t cols,
+                                   b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "gate_residual: negative shape");
+  if (rows == 0 || cols == 0) return B200Q_OK;
+  B200Q_REQUIRE(y && residual && out, B200Q_ERR_BAD_ARG, "gate_residual: null pointer");
+  B200Q_REQUIRE(ldy >= cols && ldr >= cols && ldo >= cols, B200Q_ERR_BAD_ARG, "gate_residual: leading dimension < cols");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (y_dtype) {
+    case B200Q_F32: return launch_gate<float>(y, ldy, gate, residual, ldr, out, ldo, rows, cols, st);
+    case B200Q_BF16: return launch_gate<__nv_bfloat16>(y, ldy, gate, residual, ldr, out, ldo, rows, cols, st);
+    case B200Q_F16: return launch_gate<__half>(y, ldy, gate, residual, ldr, out, ldo, rows, cols, st);
+  }
+  set_error("gate_residual: bad y_dtype %d", y_dtype);
+  return B200Q_ERR_BAD_ARG;
+}

@@ -1,0 +1,68 @@
+// W4 weight packing for the W4A8 GEMM (mixed-precision configs: weight.n_bits=[4,8],
+// ViDiT-Q/quant_utils/qdiff/base/mixed_precision_quantizer.py:56-125).
+//
+// Packed format (defined here, consumed by the in-smem unpacker of gemm_w4a8): K is split in groups of
+// 8 codes; byte i (i = 0..3) of a group's 32-bit word holds  (code[i] + 8)  in bits 0-3 and
+// (code[4+i] + 8) in bits 4-7.  The +8 bias makes nibbles unsigned so the unpack is two AND/SHIFT ops per
+// 4 codes; the GEMM epilogue folds it back through the zero-point term (zp_eff = zp_w - 8), the same
+// algebra the reference's QServe kernel uses (w4a8_per_channel_gemm_cuda_qserve.cu:290-297, 585-586).
+#include "common.cuh"
+
+namespace b200q {
+
+__global__ void __launch_bounds__(256) pack_w4_kernel(const int8_t* __restrict__ codes, int64_t ld, int64_t N, int64_t K,
+                                                       uint8_t* __restrict__ packed, int64_t ldp) {
+  const int64_t groups = (K + 7) / 8;
+  const int64_t total = N * groups;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / groups, g = i - n * groups;
+    const int8_t* src = codes + n * ld + g * 8;
+    uint32_t w = 0;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const int64_t k0 = g * 8 + b, k1 = g * 8 + 4 + b;
+      const uint32_t lo = k0 < K ? (uint32_t)(src[b] + 8) & 0xF : 8u;       // pad codes are 0 -> nibble 8
+      const uint32_t hi = k1 < K ? (uint32_t)(src[4 + b] + 8) & 0xF : 8u;
+      w |= (lo | (hi << 4)) << (8 * b);
+    }
+    *reinterpret_cast<uint32_t*>(packed + n * ldp + g * 4) = w;
+  }
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_pack_w4(const int8_t* codes, int64_t ld, int64_t N, int64_t K, uint8_t* packed, int64_t ldp,
+                             b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(N >= 0 && K >= 0, B200Q_ERR_BAD_ARG, "pack_w4: negative shape");
+  if (N == 0 || K == 0) return B200Q_OK;
+  B200Q_REQUIRE(codes && packed, B200Q_ERR_BAD_ARG, "pack_w4: null pointer");
+  B200Q_REQUIRE(ld >= K && ldp >= ((K + 7) / 8) * 4, B200Q_ERR_BAD_ARG, "pack_w4: leading dimension too small");
+  B200Q_REQUIRE(ldp % 4 == 0 && aligned(packed, 4), B200Q_ERR_BAD_ARG, "pack_w4: packed must be 4-byte aligned, ldp % 4 == 0");
+  const int64_t total = N * ((K + 7) / 8);
+  int64_t blocks = (total + 255) / 256;
+  const int64_t cap = (int64_t)sm_count() * 16;
+  if (blocks > cap) blocks = cap;
+  pack_w4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(codes, ld, N, K, packed, ldp);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
+namespace b200q {
+int gemm_w4a8_impl(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4, const float* delta_a,
+                   const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                   void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
+                   const float* residual, int64_t ldr, const float* gate, cudaStream_t st);
+}
+
+extern "C" int b200q_gemm_w4a8(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4, const float* delta_a,
+                               const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias,
+                               int bias_dtype, void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K,
+                               int epilogue, const float* residual, int64_t ldr, const float* gate,
+                               b200q_stream_t stream) {
+  clear_error();
+  return gemm_w4a8_impl(qa, lda, qw4, ldw4, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo, M,
+                        N, K, epilogue, residual, ldr, gate, (cudaStream_t)stream);
+}
