@@ -104,7 +104,7 @@ def test_quant_full_size_properties(dev):
     x = torch.randn(L, D, device=dev) * 3
     q, d, z, rs = b200q.quant_rows(x, 8, True, True)
     amax = x.abs().amax(dim=1)
-    assert torch.equal(d, amax / 127)                         # same IEEE division on the GPU
+    assert torch.equal(d, torch.div(amax, torch.full_like(amax, 127.0)))   # tensor/tensor = IEEE division (tensor/scalar multiplies by 1/127)
     assert int(q.abs().amax()) == 127                          # every row hits +-127 at its abs-max
     assert torch.equal(q.abs().amax(dim=1).int(), torch.full((L,), 127, device=dev, dtype=torch.int32))
     assert torch.equal(rs, q.sum(dim=1, dtype=torch.int32))

@@ -1,0 +1,63 @@
+"""CPU suite, build container only: the oracle restatement vs the IMPORTED, unmodified reference qdiff on fresh
+random inputs (beyond the committed golden vectors).  Runs in a subprocess because the reference package is also
+called `qdiff` and must not share an interpreter with the product mirror.  Skipped where /root/reference is absent
+(the GPU box)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+SCRIPT = r'''
+import sys, torch
+sys.path.insert(0, %(root)r)
+from oracle.ref_import import import_reference_qdiff
+from oracle import fakequant_oracle as O
+ref = import_reference_qdiff()
+from omegaconf import OmegaConf
+bq, ql, mp = ref["base_quantizer"], ref["quant_layer"], ref["mixed_precision"]
+g = torch.Generator().manual_seed(7)
+n = 0
+for trial in range(6):
+    rows, cols = [(33, 1536), (8, 8960), (64, 128), (5, 17), (128, 320), (2, 5120)][trial]
+    x = torch.randn(rows, cols, generator=g) * (torch.rand(rows, 1, generator=g) * 10 + 1e-3)
+    x[:, :: max(1, cols // 7)] *= 30
+    for bits, sym in [(8, True), (8, False), (4, True), (4, False), (6, True)]:
+        qz = bq.DynamicQuantizer(OmegaConf.create({"n_bits": bits, "sym": sym})); qz.module_name = "t"
+        codes = qz.quantize(x.clone())
+        q, d, z = O.quant_rows(x, bits, sym, True)
+        assert torch.equal(codes, q) and torch.equal(qz.delta, d) and torch.equal(qz.zero_point, z), (trial, bits, sym)
+        assert torch.equal(qz.forward(x.clone()), O.dequant_rows(q, d, z))
+        n += 1
+    for bits in (8, 4):
+        w = (torch.rand(rows, cols, generator=g) * 2 - 1) * 0.05
+        qz = bq.StaticQuantizer(OmegaConf.create({"n_bits": bits, "sym": False}))
+        deq = qz.forward(w.clone())
+        q, d, z = O.quant_rows(w, bits, False, False)
+        assert torch.equal(qz.delta, d) and torch.equal(qz.zero_point, z) and torch.equal(deq, O.dequant_rows(q, d, z))
+        n += 1
+# full layer
+for (cin, cout, wb) in [(1536, 256, 8), (320, 192, 4), (8960, 64, 8)]:
+    fp = torch.nn.Linear(cin, cout)
+    with torch.no_grad():
+        fp.bias.normal_(0, 0.02, generator=g)
+    w0 = fp.weight.detach().clone()
+    cfg = OmegaConf.create({"weight": {"n_bits": wb, "sym": False}, "act": {"n_bits": 8, "sym": True}})
+    layer = ql.QuantizedLinear(cin, cout, True, None, cfg, fp); layer.a_quantizer.module_name = "t"
+    x = torch.randn(2, 19, cin, generator=g) * 3
+    with torch.no_grad():
+        y = layer(x.clone())
+    assert torch.equal(y, O.quantized_linear_fake(x, w0, fp.bias.detach(), w_bits=wb))
+    n += 1
+print("ORACLE_PINNED", n)
+'''
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/ViDiT-Q/quant_utils/qdiff"),
+                    reason="reference tree only exists in the build container")
+def test_oracle_matches_imported_reference():
+    r = subprocess.run([sys.executable, "-c", SCRIPT % {"root": ROOT}], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-4000:]
+    assert "ORACLE_PINNED" in r.stdout

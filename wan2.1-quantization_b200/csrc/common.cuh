@@ -72,10 +72,67 @@ __device__ __forceinline__ void stg_stream4(void* p, uint32_t v) {
   asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" :: "l"(p), "r"(v) : "memory");
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2 / FMUL2 / FADD2: two fp32 lanes per issue slot on sm_100) -------
+__device__ __forceinline__ uint64_t pack_f32x2(float a, float b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t pack_u32x2(uint32_t a, uint32_t b) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack_u32x2(uint64_t v, uint32_t& a, uint32_t& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ uint64_t mul_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+// div_rn_hoisted on two lanes, then + 1.5*2^23: returns the two "integer in the mantissa" bit patterns.
+//   nd2 = (-d,-d), r2 = (r,r), magic2 = (12582912, 12582912)
+__device__ __forceinline__ uint64_t div_rn_hoisted_rne2(uint64_t x2, uint64_t nd2, uint64_t r2, uint64_t magic2) {
+  uint64_t q = mul_f32x2(x2, r2);
+  uint64_t e = fma_f32x2(q, nd2, x2);
+  q = fma_f32x2(e, r2, q);
+  e = fma_f32x2(q, nd2, x2);
+  q = fma_f32x2(e, r2, q);
+  return add_f32x2(q, magic2);
+}
+
 // Unpack one 16-byte vector of T into fp32 lanes.
 template <typename T> struct Vec16;
 template <> struct Vec16<float> {
   static constexpr int N = 4;
+  __device__ static __forceinline__ void unpack_pairs(const uint4& v, uint64_t* p) {
+    p[0] = pack_u32x2(v.x, v.y); p[1] = pack_u32x2(v.z, v.w);
+  }
+  // running statistics: amax (sym) or max/min (asym), kept in fp32
+  struct Stat { float a, b; };
+  __device__ static __forceinline__ Stat stat_init() { return {0.f, 0.f}; }
+  template <bool SYM> __device__ static __forceinline__ void stat_update(Stat& s, const uint4& v) {
+    const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+    if (SYM) {
+      s.a = fmaxf(fmaxf(fabsf(f0), fabsf(f1)), s.a);
+      s.a = fmaxf(fmaxf(fabsf(f2), fabsf(f3)), s.a);
+    } else {
+      s.a = fmaxf(fmaxf(f0, f1), s.a); s.a = fmaxf(fmaxf(f2, f3), s.a);
+      s.b = fminf(fminf(f0, f1), s.b); s.b = fminf(fminf(f2, f3), s.b);
+    }
+  }
+  __device__ static __forceinline__ void stat_final(const Stat& s, float& a, float& b) { a = s.a; b = s.b; }
   __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
     f[0] = __uint_as_float(v.x); f[1] = __uint_as_float(v.y);
     f[2] = __uint_as_float(v.z); f[3] = __uint_as_float(v.w);
@@ -83,6 +140,34 @@ template <> struct Vec16<float> {
 };
 template <> struct Vec16<__nv_bfloat16> {
   static constexpr int N = 8;
+  __device__ static __forceinline__ void unpack_pairs(const uint4& v, uint64_t* p) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) p[i] = pack_u32x2(w[i] << 16, w[i] & 0xffff0000u);
+  }
+  // statistics stay packed in bf16x2 (max/min of bf16 values is exact), one 3-input VHMNMX per 4 elements
+  struct Stat { __nv_bfloat162 a, b; };
+  __device__ static __forceinline__ Stat stat_init() {
+    Stat s; s.a = __float2bfloat162_rn(0.f); s.b = __float2bfloat162_rn(0.f); return s;
+  }
+  template <bool SYM> __device__ static __forceinline__ void stat_update(Stat& s, const uint4& v) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (SYM) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] &= 0x7fff7fffu;
+    }
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(w);
+    s.a = __hmax2(__hmax2(h[0], h[1]), s.a);
+    s.a = __hmax2(__hmax2(h[2], h[3]), s.a);
+    if (!SYM) {
+      s.b = __hmin2(__hmin2(h[0], h[1]), s.b);
+      s.b = __hmin2(__hmin2(h[2], h[3]), s.b);
+    }
+  }
+  __device__ static __forceinline__ void stat_final(const Stat& s, float& a, float& b) {
+    a = fmaxf(__low2float(s.a), __high2float(s.a));
+    b = fminf(__low2float(s.b), __high2float(s.b));
+  }
   __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -94,6 +179,36 @@ template <> struct Vec16<__nv_bfloat16> {
 };
 template <> struct Vec16<__half> {
   static constexpr int N = 8;
+  __device__ static __forceinline__ void unpack_pairs(const uint4& v, uint64_t* p) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&w[i]));
+      p[i] = pack_f32x2(t.x, t.y);
+    }
+  }
+  struct Stat { __half2 a, b; };
+  __device__ static __forceinline__ Stat stat_init() {
+    Stat s; s.a = __float2half2_rn(0.f); s.b = __float2half2_rn(0.f); return s;
+  }
+  template <bool SYM> __device__ static __forceinline__ void stat_update(Stat& s, const uint4& v) {
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    if (SYM) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) w[i] &= 0x7fff7fffu;
+    }
+    const __half2* h = reinterpret_cast<const __half2*>(w);
+    s.a = __hmax2(__hmax2(h[0], h[1]), s.a);
+    s.a = __hmax2(__hmax2(h[2], h[3]), s.a);
+    if (!SYM) {
+      s.b = __hmin2(__hmin2(h[0], h[1]), s.b);
+      s.b = __hmin2(__hmin2(h[2], h[3]), s.b);
+    }
+  }
+  __device__ static __forceinline__ void stat_final(const Stat& s, float& a, float& b) {
+    a = fmaxf(__low2float(s.a), __high2float(s.a));
+    b = fminf(__low2float(s.b), __high2float(s.b));
+  }
   __device__ static __forceinline__ void unpack(const uint4& v, float* f) {
     const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll

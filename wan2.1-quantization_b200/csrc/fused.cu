@@ -106,17 +106,29 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
     const int j = v * tpr + t;
     const bool live = j < kv;
     const int c0 = j * N;
+    // per-channel vectors as 16-byte loads (L1/L2 resident: cols*4 bytes, shared by every row)
+    float pw[N], pb[N], psc[N], psh[N];
+#pragma unroll
+    for (int h = 0; h < N / 4; ++h) {
+      const int c = live ? c0 + 4 * h : 0;
+      const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+      const float4 w4 = a.ln_w ? __ldg(reinterpret_cast<const float4*>(a.ln_w + c)) : one;
+      const float4 b4 = a.ln_b ? __ldg(reinterpret_cast<const float4*>(a.ln_b + c)) : zero;
+      const float4 s4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + c)) : zero;
+      const float4 h4 = a.shift ? __ldg(reinterpret_cast<const float4*>(a.shift + c)) : zero;
+      pw[4 * h] = w4.x; pw[4 * h + 1] = w4.y; pw[4 * h + 2] = w4.z; pw[4 * h + 3] = w4.w;
+      pb[4 * h] = b4.x; pb[4 * h + 1] = b4.y; pb[4 * h + 2] = b4.z; pb[4 * h + 3] = b4.w;
+      psc[4 * h] = s4.x; psc[4 * h + 1] = s4.y; psc[4 * h + 2] = s4.z; psc[4 * h + 3] = s4.w;
+      psh[4 * h] = h4.x; psh[4 * h + 1] = h4.y; psh[4 * h + 2] = h4.z; psh[4 * h + 3] = h4.w;
+    }
 #pragma unroll
     for (int i = 0; i < N; ++i) {
       float y = (f[v][i] - mean) * rstd;
-      if (live) {
-        if (a.ln_w) y = __fmul_rn(y, a.ln_w[c0 + i]);
-        if (a.ln_b) y = __fadd_rn(y, a.ln_b[c0 + i]);
-        if (a.scale) y = __fmul_rn(y, __fadd_rn(1.f, a.scale[c0 + i]));   // ln*(1+e1)   model.py:327
-        if (a.shift) y = __fadd_rn(y, a.shift[c0 + i]);                   //  + e0
-      } else {
-        y = 0.f;
-      }
+      if (a.ln_w) y = __fmul_rn(y, pw[i]);
+      if (a.ln_b) y = __fadd_rn(y, pb[i]);
+      if (a.scale) y = __fmul_rn(y, __fadd_rn(1.f, psc[i]));   // ln*(1+e1)   model.py:327
+      if (a.shift) y = __fadd_rn(y, psh[i]);                   //  + e0
+      y = live ? y : 0.f;
       f[v][i] = y;
       amax = fmaxf(amax, fabsf(y));
     }
@@ -132,6 +144,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   float delta = __fdiv_rn(amax, a.n_levels);
   if (delta < 1.0e-6f) delta = 1.0e-6f;                                   // base_quantizer.py:122-128
   const float r = __frcp_rn(delta);
+  const uint64_t r2 = pack_f32x2(r, r), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
   int8_t* qrow = a.q + (row_ok ? row : 0) * a.ldq;
   int sum = 0;
 #pragma unroll
@@ -140,10 +153,13 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
     uint32_t packed[N / 4];
 #pragma unroll
     for (int g = 0; g < N / 4; ++g) {
-      int c[4];
+      uint32_t c[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) c[i] = rne_to_int_bits(div_rn_hoisted(f[v][4 * g + i], delta, r));
-      packed[g] = pack4i(c[0], c[1], c[2], c[3]);
+      for (int i = 0; i < 2; ++i) {
+        const uint64_t qb = div_rn_hoisted_rne2(pack_f32x2(f[v][4 * g + 2 * i], f[v][4 * g + 2 * i + 1]), nd2, r2, magic2);
+        unpack_u32x2(qb, c[2 * i], c[2 * i + 1]);
+      }
+      packed[g] = pack4i((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
       sum = __dp4a((int)packed[g], 0x01010101, sum);
     }
     if (row_ok && j < kv) {
@@ -270,6 +286,9 @@ extern "C" int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int6
   B200Q_REQUIRE(cols % vecn == 0 && ldx % vecn == 0 && aligned(x, 16), B200Q_ERR_UNSUPPORTED,
                 "ln_mod_quant: cols and ldx must be multiples of %d and x 16-byte aligned", vecn);
   B200Q_REQUIRE(q == nullptr || (ldq % vecn == 0 && aligned(q, vecn)), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: q misaligned");
+  B200Q_REQUIRE((!ln_w || aligned(ln_w, 16)) && (!ln_b || aligned(ln_b, 16)) && (!shift || aligned(shift, 16)) &&
+                    (!scale || aligned(scale, 16)),
+                B200Q_ERR_BAD_ARG, "ln_mod_quant: per-channel vectors must be 16-byte aligned");
   LnArgs a{};
   a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps;
   a.shift = shift; a.scale = scale; a.n_levels = (float)((1 << (n_bits - 1)) - 1);

@@ -84,16 +84,10 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
     delta = row_ok ? a.delta[row] : 1.f;
     zp = row_ok ? a.zero_point[row] : 0.f;
   } else {
+    typename VT::Stat st = VT::stat_init();
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-      float f[N];
-      VT::unpack(raw[v], f);
-#pragma unroll
-      for (int i = 0; i < N; ++i) {
-        if (MODE == kSymDyn) s0 = fmaxf(s0, fabsf(f[i]));
-        else { s0 = fmaxf(s0, f[i]); s1 = fminf(s1, f[i]); }
-      }
-    }
+    for (int v = 0; v < V; ++v) VT::template stat_update<MODE == kSymDyn>(st, raw[v]);
+    VT::stat_final(st, s0, s1);
     s0 = warp_max(s0);
     if (MODE == kAsymDyn) s1 = warp_min(s1);
     if (warps_per_row > 1) {
@@ -109,30 +103,32 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
   }
 
   const float r = __frcp_rn(delta);
-  const int zpi = __float2int_rn(zp);
+  const uint64_t r2 = pack_f32x2(r, r), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+  const int zpi = __float2int_rn(zp) + 0x4B400000;      // also strips the magic-number exponent bits
   const int lo = (int)a.clamp_lo, hi = (int)a.clamp_hi;
   int8_t* qrow = a.q + (row_ok ? row : 0) * a.ldq;
   int sum = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int j = v * tpr + t;
-    float f[N];
-    VT::unpack(raw[v], f);
+    uint64_t xp[N / 2];
+    VT::unpack_pairs(raw[v], xp);
     uint32_t packed[N / 4];
 #pragma unroll
     for (int g = 0; g < N / 4; ++g) {
-      int c[4];
+      uint32_t c[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const float qf = div_rn_hoisted(f[4 * g + i], delta, r);
-        if (MODE == kSymDyn) {
-          c[i] = rne_to_int_bits(qf);          // |x/delta| <= n_levels: no clamp, low byte is the code
-        } else {
-          c[i] = min(max(rne_to_int(qf) - zpi, lo), hi);
-        }
+      for (int i = 0; i < 2; ++i) {
+        // exact RN(x/delta) on two lanes (FFMA2), then round-half-even via the magic-number add
+        const uint64_t qb = div_rn_hoisted_rne2(xp[2 * g + i], nd2, r2, magic2);
+        unpack_u32x2(qb, c[2 * i], c[2 * i + 1]);
       }
-      packed[g] = pack4(c[0], c[1], c[2], c[3]);
-      sum = __dp4a((int)packed[g], 0x01010101, sum);
+      if (MODE != kSymDyn) {                    // sym dynamic: |x/delta| <= n_levels, the low byte is the code
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = (uint32_t)min(max((int)c[i] - zpi, lo), hi);
+      }
+      packed[g] = pack4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
+      if (j < kv) sum = __dp4a((int)packed[g], 0x01010101, sum);
     }
     if (row_ok && j < kv) {
       if (N == 4) stg_stream4(qrow + (int64_t)j * N, packed[0]);
