@@ -1,0 +1,318 @@
+#!/usr/bin/env python
+"""bench.py — W8A8 Wan2.1 DiT-step benchmark (BASELINE.json metric / configs[1]).
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU fake-quant path on the host cores
+
+One "step" = one WanModel.forward (one CFG branch) of Wan2.1-T2V-1.3B, 30 blocks, all ten linears of every block
+W8A8 (per-out-channel asymmetric weights, per-token symmetric activations), 832x480x81 synthetic latent =
+32,760 tokens, random-init weights.  Prints ONE JSON line (see the contract in the task statement):
+  value    : ms per step with inputs resident in HBM (CUDA events, max over ranks)
+  e2e      : same through the public API with HOST (pinned) inputs, H2D + D2H inside the timed region
+  roofline : dominant kernel = the tcgen05 int8 GEMM; achieved TOPS from CUDA events around every launch
+  cpu_baseline : the oracle port of the reference fake-quant block timed on the host cores (bounded sample)
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "wan2.1-quantization_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+METRIC = "W8A8 DiT-step ms (Wan2.1-T2V-1.3B, 30 blocks, 32760 tokens)"
+WORKLOAD = ("Wan2.1-T2V-1.3B full 30-block DiT W8A8 denoising step on B200, 832x480x81 synthetic latent "
+            "(16x21x60x104 -> 32760 tokens), one CFG branch; BASELINE.json configs[1]")
+LATENT_SHAPE = (16, 21, 60, 104)
+TEXT_TOKENS, TEXT_DIM = 512, 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--layers", type=int, default=None, help="debug only: fewer blocks (result is then marked invalid)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except (ValueError, IndexError):
+                continue
+            for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                if len(r) > col and r[col].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle port of the reference fake-quant block on the host cores
+# ------------------------------------------------------------------------------------------------------------
+def cpu_reference_step_ms(L=32760, rows_sample=2048, q_sample=512, repeats=3, layers=30):
+    """Bounded sample of configs[1] on the CPU (reference arithmetic: fp32 fake-quant, quant_layer.py:57-74 through the
+    oracle port).  Token-local stages (LN/modulate, ten fake-quant linears, GELU, residuals, cross-attention) are
+    timed on `rows_sample` of the L tokens and scaled by L/rows_sample; self-attention is timed for `q_sample`
+    queries against all L keys and scaled by L/q_sample; one block x `layers`."""
+    import torch.nn.functional as F
+    from oracle import fakequant_oracle as O
+    torch.set_num_threads(os.cpu_count())
+    D, Fd, H = 1536, 8960, 12
+    p = O.make_block_params(D, Fd, seed=0)
+    blk = O.WanBlockOracle(p, D, Fd, H)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(rows_sample, D, generator=g)
+    e = torch.randn(6, D, generator=g) * 0.1
+    ctx = torch.randn(TEXT_TOKENS, D, generator=g)
+    grid = (21, 30, 52)
+
+    def token_local():
+        # WanBlockOracle.forward with the self-attention core replaced by identity on v (timed separately below)
+        blk.attention = lambda q, k, v: v.flatten(1)
+        return blk.forward(x, e, grid, ctx)
+
+    qh = torch.randn(1, H, q_sample, D // H, generator=g)
+    kh = torch.randn(1, H, L, D // H, generator=g)
+    vh = torch.randn(1, H, L, D // H, generator=g)
+
+    def attn():
+        return F.scaled_dot_product_attention(qh, kh, vh)
+
+    def med(fn):
+        fn()
+        ts = []
+        for _ in range(repeats):
+            t0 = time.perf_counter(); fn(); ts.append(time.perf_counter() - t0)
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    with torch.no_grad():
+        t_local, t_attn = med(token_local), med(attn)
+    block_ms = 1e3 * (t_local * L / rows_sample + t_attn * L / q_sample)
+    sample = (f"1 of {layers} blocks: token-local stages on {rows_sample}/{L} tokens ({t_local * 1e3:.0f} ms) + self-attention "
+              f"on {q_sample}/{L} queries x {L} keys ({t_attn * 1e3:.0f} ms), each scaled linearly to L, x{layers} blocks; "
+              f"fp32 torch CPU, median of {repeats}")
+    return block_ms * layers, sample
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps = max(1, min(args.steps, 3))
+    ms, sample = cpu_reference_step_ms(repeats=max(1, steps))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32 (CPU fake-quant)", "data": "synthetic", "config": {"workload": WORKLOAD, "parallelism": "cpu"},
+        "cpu_baseline": {"value": ms, "unit": "ms", "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": ms, "unit": "ms", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    import b200q
+    from wan import model as M
+    from wan.parallel import SequenceParallel, exchange_bytes_per_rank
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl b200 needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    b200q.load()
+    rc = b200q.load().b200q_device_info(None, None, None)
+    if rc != 0:
+        raise SystemExit("libb200q: " + b200q.load().b200q_last_error().decode())
+
+    cfg = M.WAN_1_3B
+    sp = SequenceParallel() if world > 1 else None
+    dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers)
+    L = (LATENT_SHAPE[1] // 1) * (LATENT_SHAPE[2] // 2) * (LATENT_SHAPE[3] // 2)
+
+    g = torch.Generator().manual_seed(0)
+    lat_h = torch.randn(*LATENT_SHAPE, generator=g).pin_memory()
+    ctx_h = torch.randn(TEXT_TOKENS, TEXT_DIM, generator=g).pin_memory()
+    t_h = torch.tensor([500.0]).pin_memory()
+    out_h = torch.empty(*LATENT_SHAPE).pin_memory()
+    lat_d, ctx_d, t_d = lat_h.to(dev), ctx_h.to(dev), t_h.to(dev)
+
+    # --- instrument the dominant kernel: CUDA events around every quantized-GEMM launch --------------------------
+    gemm_events = []
+    orig_qlinear = M.qlinear
+
+    def timed_qlinear(qa, da, rowsum, w, *a, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        y = orig_qlinear(qa, da, rowsum, w, *a, **kw)
+        e.record()
+        gemm_events.append((s, e, 2.0 * qa.shape[0] * w.N * w.K, (qa.shape[0], w.N, w.K)))
+        return y
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_resident():
+        return dit.forward(lat_d, t_d, ctx_d)
+
+    def step_e2e():
+        lat = lat_h.to(dev, non_blocking=True)
+        ctx = ctx_h.to(dev, non_blocking=True)
+        t = t_h.to(dev, non_blocking=True)
+        y = dit.forward(lat, t, ctx)
+        out_h.copy_(y, non_blocking=True)
+        return y
+
+    for _ in range(max(args.warmup, 3)):
+        step_resident()
+    sync_all()
+
+    clocks = ClockSampler(local)
+    clocks.start()
+    M.qlinear = timed_qlinear
+    launches0 = b200q.launch_count
+    sync_all()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(args.steps):
+        step_resident()
+    ev1.record()
+    sync_all()
+    launches = b200q.launch_count - launches0
+    M.qlinear = orig_qlinear
+    ms = ev0.elapsed_time(ev1) / args.steps
+
+    # dominant-kernel accounting
+    g_ms = sum(s.elapsed_time(e) for s, e, _, _ in gemm_events)
+    g_ops = sum(o for _, _, o, _ in gemm_events)
+    by_shape = {}
+    for s, e, o, shp in gemm_events:
+        a = by_shape.setdefault("x".join(map(str, shp)), [0.0, 0.0, 0])
+        a[0] += s.elapsed_time(e); a[1] += o; a[2] += 1
+    gemm_events.clear()
+
+    # e2e: host buffers, H2D + D2H inside the timed region
+    step_e2e(); sync_all()
+    ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev2.record()
+    for _ in range(args.steps):
+        step_e2e()
+    ev3.record()
+    sync_all()
+    e2e_ms = ev2.elapsed_time(ev3) / args.steps
+    clk = clocks.stop()
+
+    if world > 1:
+        tmax = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = float(tmax[0]), float(tmax[1])
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:  # noqa: BLE001
+            pass
+        bf16_sus = peaks.get("bf16_tflops_sustained")
+        if bf16_sus:
+            peak, peak_src = 2.0 * bf16_sus, "2 x MEASURED_PEAKS.json bf16_tflops_sustained (kind::i8 issues at 2x the bf16 rate)"
+        else:
+            peak, peak_src = 2.0 * 1400.0, "fallback: 2 x 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)"
+        achieved = g_ops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        out = {
+            "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
+            "dtype": "int8 (s32 accumulate, bf16 attention core)", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "parallelism": f"ulysses{world}" if world > 1 else "single-gpu",
+                       "weights": "random-init, replicated", "l2": "per-step working set (>=200 MB per stage) >> 126 MB L2; no flush needed",
+                       "cfg_branches_per_step": 1},
+            "clocks": clk,
+            "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": lat_h.numel() * 4 + ctx_h.numel() * 4 + 4,
+                    "d2h_bytes_per_step": out_h.numel() * 4},
+            "gpu_launches": launches,
+            "roofline": {"bound": "tensor", "kernel": "gemm_w8a8_kernel (tcgen05.mma.kind::i8)", "achieved": achieved,
+                         "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+                         "peak_source": peak_src, "frac_of_nominal_4500": achieved / 4500.0,
+                         "gemm_share_of_step": g_ms / (ms * args.steps),
+                         "by_shape_tops": {k: v[1] / (v[0] * 1e-3) / 1e12 for k, v in by_shape.items() if v[0] > 0}},
+        }
+        if world > 1:
+            b, pu, pr = exchange_bytes_per_rank(L, cfg.dim, world, cfg.num_heads)
+            out["config"]["exchange_bytes_per_rank_per_block"] = b
+            out["config"]["head_plan"] = f"Pu={pu} x Pr={pr}"
+        if args.layers is not None and args.layers != cfg.num_layers:
+            out["invalid"] = f"debug run with {args.layers} of {cfg.num_layers} blocks"
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                cms, sample = cpu_reference_step_ms()
+                out["cpu_baseline"] = {"value": cms, "unit": "ms", "cores": os.cpu_count(), "kind": "port", "sample": sample}
+            except Exception as ex:  # noqa: BLE001
+                out["cpu_baseline"] = {"value": None, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
+                                       "sample": "failed: " + repr(ex)}
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)

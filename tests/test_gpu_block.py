@@ -1,0 +1,78 @@
+"""-m gpu: one quantized Wan DiT block through the integer runtime vs the fp32 fake-quant oracle block
+(oracle.fakequant_oracle.WanBlockOracle = restated wan/modules/model.py:293-370 with the imported-reference-pinned
+quantizers).  Tolerance (north_star): cosine >= 0.999 on the block output; max relative error stated below."""
+import pytest
+import torch
+
+import b200q
+from oracle import fakequant_oracle as O
+from wan import model as M
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm()))
+
+
+@pytest.mark.parametrize("dim,ffn,heads,grid", [(256, 512, 2, (2, 6, 8)), (384, 1024, 3, (3, 4, 4))])
+def test_block_matches_oracle(dev, dim, ffn, heads, grid):
+    cfg = M.WanConfig(dim=dim, ffn_dim=ffn, num_heads=heads, num_layers=1)
+    p = O.make_block_params(dim, ffn, seed=0)
+    L, T = grid[0] * grid[1] * grid[2], 32
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(L, dim, generator=g)
+    e = torch.randn(6, dim, generator=g) * 0.1
+    ctx = torch.randn(T, dim, generator=g)
+    ref = O.WanBlockOracle(p, dim, ffn, heads).forward(x.clone(), e, grid, ctx)
+
+    blk = M.WanBlockQ.from_fp_params(cfg, p)
+    cos, sin = M.rope_table(dim // heads, grid, dev)
+    out = blk.forward(x.clone().to(dev), e.to(dev), ctx.to(dev), cos, sin).cpu()
+    c = _cos(out, ref)
+    rel = float((out - ref).abs().max() / ref.abs().max())
+    assert c >= 0.999, c
+    assert rel <= 5e-2, rel          # bf16 intermediates (q,k,v, attention, GELU output) vs the oracle's fp32
+
+
+def test_block_weight_codes_bit_exact(dev):
+    dim, ffn = 256, 512
+    p = O.make_block_params(dim, ffn, seed=3)
+    cfg = M.WanConfig(dim=dim, ffn_dim=ffn, num_heads=2, num_layers=1)
+    blk = M.WanBlockQ.from_fp_params(cfg, p)
+    for name, w in (("ffn.0", blk.w_f0), ("ffn.2", blk.w_f2), ("self_attn.o", blk.w_o)):
+        q, d, z = O.quant_rows(p[name + ".weight"], 8, False, dynamic=False)
+        assert torch.equal(w.codes.cpu().float(), q) and torch.equal(w.delta.cpu(), d.flatten())
+        assert torch.equal(w.zp.cpu(), z.flatten())
+    q, d, z = O.quant_rows(p["self_attn.k.weight"], 8, False, dynamic=False)
+    assert torch.equal(blk.w_qkv.codes[dim:2 * dim].cpu().float(), q)
+
+
+def test_dit_forward_runs_and_is_deterministic(dev):
+    cfg = M.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, freq_dim=64)
+    dit = M.WanDiTQ.random(cfg, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lat = torch.randn(16, 3, 8, 12, device=dev, generator=g)
+    ctx = torch.randn(20, 64, device=dev, generator=g)
+    t = torch.tensor([500.0], device=dev)
+    y1 = dit.forward(lat, t, ctx)
+    y2 = dit.forward(lat, t, ctx)
+    assert y1.shape == lat.shape and torch.isfinite(y1).all()
+    assert torch.equal(y1, y2)
+
+
+def test_calibration_collector(dev):
+    import torch.nn as nn
+    from wan.calibration import CalibrationCollector
+    m = nn.Sequential(nn.Linear(64, 128), nn.GELU(), nn.Linear(128, 32)).to(dev)
+    col = CalibrationCollector(m)
+    xs = [torch.randn(3, 50, 64, device=dev) * (i + 1) for i in range(3)]
+    ref0, ref1 = [], []
+    for x in xs:
+        ref0.append(O.calib_absmax(x.cpu()))
+        ref1.append(O.calib_absmax(m[1](m[0](x)).detach().cpu()))
+        m(x)
+    sd = col.state_dict()
+    assert torch.equal(sd["0"].max(dim=0)[0], O.calib_merge(ref0))
+    assert torch.equal(sd["2"].max(dim=0)[0], O.calib_merge(ref1))

@@ -1,0 +1,77 @@
+"""CPU suite, world_size 2 and 4 over gloo: the sequence-parallel attention exchange (wan/parallel.py) reproduces
+single-process attention exactly (pure permutation + the same attention core), including the P = Pu x Pr hybrid used
+when the head count does not divide by P, and the calibration allreduce(MAX) equals the unsharded statistic."""
+import os
+import socket
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _cpu_attention(q, k, v, heads):
+    Lq, hd = q.shape[0], q.shape[1] // heads
+    qh, kh, vh = (t.view(-1, heads, hd).permute(1, 0, 2).unsqueeze(0) for t in (q, k, v))
+    o = torch.nn.functional.scaled_dot_product_attention(qh, kh, vh)
+    return o.squeeze(0).permute(1, 0, 2).reshape(Lq, heads * hd)
+
+
+def _worker(rank, world, port, heads, L, hd, out_q):
+    sys.path.insert(0, os.path.join(ROOT, "wan2.1-quantization_b200"))
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from wan.parallel import SequenceParallel
+    torch.manual_seed(0)
+    D = heads * hd
+    q, k, v = (torch.randn(L, D) for _ in range(3))
+    full = _cpu_attention(q, k, v, heads)
+    sp = SequenceParallel(attention_core=_cpu_attention)
+    (qs, off, Lr), (ks, _, _), (vs, _, _) = sp.shard_tokens(q), sp.shard_tokens(k), sp.shard_tokens(v)
+    o = sp.attention(qs.contiguous(), ks.contiguous(), vs.contiguous(), heads)
+    ok_attn = torch.allclose(o, full[off:off + Lr], rtol=1e-5, atol=1e-6)
+    gathered = sp.gather_tokens(o, L)
+    ok_gather = torch.allclose(gathered, full, rtol=1e-5, atol=1e-6)
+    # calibration: sharded rows + allreduce(MAX) == unsharded abs-max, bit for bit
+    x = torch.randn(L, 48)
+    stat = x[off:off + Lr].abs().max(dim=0)[0]
+    sp.allreduce_max(stat)
+    ok_cal = torch.equal(stat, x.abs().max(dim=0)[0])
+    out_q.put((rank, ok_attn, ok_gather, ok_cal, sp.plan(heads)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,heads", [(2, 4), (4, 12), (4, 6), (2, 3)])
+def test_sequence_parallel_attention_gloo(world, heads):
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, heads, 48, 8, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_attn, ok_gather, ok_cal, plan in res:
+        assert ok_attn and ok_gather and ok_cal, (rank, ok_attn, ok_gather, ok_cal, plan)
+
+
+def test_head_plan():
+    from wan.parallel import _largest_head_divisor, exchange_bytes_per_rank
+    assert _largest_head_divisor(8, 12) == 4 and _largest_head_divisor(4, 12) == 4 and _largest_head_divisor(8, 40) == 8
+    b, pu, pr = exchange_bytes_per_rank(75600, 5120, 8, 40)
+    assert (pu, pr) == (8, 1)
+    # 14B P=8 sends (P-1)/P * (L/P)*D*2 = 84.7 MB per tensor per rank
+    per_tensor = (8 - 1) / 8 * (75600 / 8) * 5120 * 2
+    assert abs(b - 4 * per_tensor) < 1e-6 * b

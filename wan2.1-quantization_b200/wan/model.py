@@ -1,0 +1,378 @@
+"""B200-native runtime for the quantized Wan2.1 DiT forward ("DiT step").
+
+This is the counterpart of the reference's `hardware_forward_refactor` + `WanAttentionBlockWithCudaKernel`
+(ViDiT-Q/examples/Wan2.1/wan/quant_wanx.py:188-228, wan/quant_wanx_cuda.py:136-310), which swaps the model's
+blocks for kernel-backed ones after PTQ.  The reference's version only runs self-attn q/k/v in int8
+(`use_kernel=[True,False,False]`, quant_wanx_cuda.py:136) and cannot launch its LN kernel for dim > 4096; here
+all ten linears of a block are integer GEMMs and every token-local stage is one fused kernel:
+
+    x (fp32 residual stream, [L, D])
+      ln_mod_quant(norm1, e0/e1)            -> int8 codes, per-token delta, rowsum        (1 kernel)
+      gemm_w8a8  [L,D]x[3D,D]  (q|k|v fused: same activation codes)        -> bf16 [L,3D]  (1 kernel)
+      RMSNorm(q), RMSNorm(k) over D, 3-axis RoPE (model.py:43-89)                          (torch ops; next-row f-4)
+      attention                                                   (library flash attention, or the int8 path)
+      quant_rows(attn_out) -> gemm_w8a8 'o' with epilogue x += y*e2                        (2 kernels)
+      ln_mod_quant(norm3 affine) -> q gemm ; context: quant_rows -> [T,D]x[2D,D] k|v gemm ; attention ; o gemm (+x)
+      ln_mod_quant(norm2, e3/e4) -> gemm + GELU epilogue -> quant_rows -> gemm with epilogue x += y*e5
+
+Sequence parallelism (Ulysses, wan/distributed/xdit_context_parallel.py:66-192): every stage above is token-local,
+so ranks own contiguous token chunks and only attention exchanges data (wan/parallel.py).
+
+Numerics contract: int8 codes and int32 accumulators are bit-exact w.r.t. the fake-quant oracle;
+bf16 block outputs agree to cosine >= 0.999.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+import b200q
+
+
+@dataclass
+class WanConfig:
+    """Hyper-parameters of examples/Wan2.1/wan/configs/wan_t2v_{1_3B,14B}.py:20-29."""
+    dim: int = 1536
+    ffn_dim: int = 8960
+    num_heads: int = 12
+    num_layers: int = 30
+    in_dim: int = 16
+    out_dim: int = 16
+    text_dim: int = 4096
+    text_len: int = 512
+    freq_dim: int = 256
+    patch_size: tuple = (1, 2, 2)
+    eps: float = 1e-6
+    name: str = "Wan2.1-T2V-1.3B"
+
+    @property
+    def head_dim(self):
+        return self.dim // self.num_heads
+
+
+WAN_1_3B = WanConfig()
+WAN_14B = WanConfig(dim=5120, ffn_dim=13824, num_heads=40, num_layers=40, name="Wan2.1-T2V-14B")
+
+
+# ------------------------------------------------------------------------------------------------------------
+# quantized weight bundle
+# ------------------------------------------------------------------------------------------------------------
+class QWeight:
+    """int8 (or packed int4) codes [N,K] + fp32 per-out-channel delta / zero_point + fp32 bias: what
+    `quantize_and_save_weight_` exports (quant_wanx_cuda.py:39-55), kept in fp32 scales to match the fake-quant path."""
+
+    def __init__(self, codes, delta, zp, bias, n_bits=8, packed=None, K=None):
+        self.codes, self.delta, self.zp, self.bias, self.n_bits, self.packed = codes, delta, zp, bias, n_bits, packed
+        self.N = codes.shape[0] if codes is not None else packed.shape[0]
+        self.K = K if K is not None else codes.shape[1]
+
+    @staticmethod
+    def from_fp(weight, bias, n_bits=8, sym=False):
+        """StaticQuantizer.init_quant_params + quantize on device (base_quantizer.py:58-99)."""
+        w = weight.detach().float().cuda()
+        codes, delta, zp, _ = b200q.quant_rows(w, n_bits, sym, dynamic=False, want_rowsum=False)
+        packed = b200q.pack_w4(codes) if n_bits <= 4 else None
+        b = None if bias is None else bias.detach().float().cuda().contiguous()
+        return QWeight(codes, delta, None if sym else zp, b, n_bits, packed)
+
+    @staticmethod
+    def from_quantized_linear(layer):
+        """Build from a qdiff QuantizedLinear (after PTQ / load_quant_param_dict)."""
+        st = layer.int_weight_state(torch.device("cuda", torch.cuda.current_device()))
+        b = None if layer.bias is None else layer.bias.detach().float().cuda().contiguous()
+        return QWeight(st["codes"], st["delta"], st["zp"], b, st["n_bits"], st["packed"])
+
+    @staticmethod
+    def cat(ws):
+        """Stack along N (q|k|v share their activation codes -> one GEMM)."""
+        assert all(w.n_bits == ws[0].n_bits and w.K == ws[0].K for w in ws)
+        codes = torch.cat([w.codes for w in ws], 0)
+        zp = None if ws[0].zp is None else torch.cat([w.zp for w in ws], 0)
+        bias = None if ws[0].bias is None else torch.cat([w.bias for w in ws], 0)
+        packed = b200q.pack_w4(codes) if ws[0].n_bits <= 4 else None
+        return QWeight(codes, torch.cat([w.delta for w in ws], 0), zp, bias, ws[0].n_bits, packed)
+
+    @staticmethod
+    def random(N, K, n_bits=8, device="cuda", generator=None, with_zp=True):
+        """Random-init weights generated directly as codes + scales (14B would need 56 GB in fp32)."""
+        hi = 2 ** (n_bits - 1)
+        codes = torch.randint(-hi, hi, (N, K), dtype=torch.int8, device=device, generator=generator)
+        bound = math.sqrt(6.0 / (N + K))                      # xavier-uniform range (model.py:663-667)
+        delta = torch.full((N,), 2 * bound / (2 ** n_bits - 1), device=device) * \
+            (0.9 + 0.2 * torch.rand(N, device=device, generator=generator))
+        zp = torch.randint(-1, 2, (N,), device=device, generator=generator).float() if with_zp else None
+        bias = torch.randn(N, device=device, generator=generator) * 0.02
+        packed = b200q.pack_w4(codes) if n_bits <= 4 else None
+        return QWeight(codes, delta, zp, bias, n_bits, packed)
+
+    def nbytes(self):
+        return (self.packed.numel() if self.packed is not None else self.codes.numel())
+
+
+def qlinear(qa, da, rowsum, w: QWeight, out_dtype=torch.bfloat16, epilogue=b200q.EPI_NONE, residual=None, gate=None):
+    if w.packed is not None:
+        return b200q.gemm_w4a8(qa, w.packed, w.K, da, w.delta, w.zp, rowsum, w.bias, out_dtype=out_dtype,
+                               epilogue=epilogue, residual=residual, gate=gate)
+    return b200q.gemm_w8a8(qa, w.codes, da, w.delta, w.zp, rowsum, w.bias, out_dtype=out_dtype, epilogue=epilogue,
+                           residual=residual, gate=gate)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# RoPE tables / RMSNorm (host-of-the-path pieces; fp32/bf16 torch ops)
+# ------------------------------------------------------------------------------------------------------------
+def rope_table(head_dim, grid, device, pos_offset=0, length=None):
+    """cos/sin [L, head_dim/2] fp32 for the 3-axis RoPE of model.py:31-70, 527-533 (computed in float64).
+    pos_offset/length select a rank's token chunk (xdit_context_parallel.py:52-58)."""
+    d = head_dim
+    dims = [d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)]
+
+    def ang(n, dim):
+        inv = 1.0 / torch.pow(10000, torch.arange(0, dim, 2, dtype=torch.float64).div(dim))
+        return torch.outer(torch.arange(n, dtype=torch.float64), inv)
+
+    f, h, w = grid
+    a = torch.cat([ang(f, dims[0]).view(f, 1, 1, -1).expand(f, h, w, -1),
+                   ang(h, dims[1]).view(1, h, 1, -1).expand(f, h, w, -1),
+                   ang(w, dims[2]).view(1, 1, w, -1).expand(f, h, w, -1)], dim=-1).reshape(f * h * w, -1)
+    if length is not None:
+        a = a[pos_offset:pos_offset + length]
+    return a.cos().float().to(device).contiguous(), a.sin().float().to(device).contiguous()
+
+
+def rmsnorm_rope(x, weight, eps, cos=None, sin=None, num_heads=1):
+    """WanRMSNorm over the FULL model dim (model.py:73-89, 127-128) then optional RoPE on [L, H, hd] pairs.
+    x bf16 [L, D] (may be a strided column slice) -> bf16 [L, D] contiguous."""
+    xf = x.float()
+    y = xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + eps)
+    y = y.to(x.dtype).float() * weight                       # .type_as(x) * weight
+    if cos is not None:
+        L, D = y.shape
+        yp = y.view(L, num_heads, D // num_heads // 2, 2)
+        a, b = yp[..., 0], yp[..., 1]
+        c, s = cos[:, None, :], sin[:, None, :]
+        y = torch.stack((a * c - b * s, a * s + b * c), dim=-1).view(L, D)
+    return y.to(torch.bfloat16)
+
+
+def sdpa(q, k, v, num_heads):
+    """q [Lq, H*hd], k,v [Lk, H*hd] bf16 -> [Lq, H*hd] bf16 via the library flash attention
+    (the reference calls flash-attn, wan/modules/attention.py:94-127)."""
+    Lq, Lk = q.shape[0], k.shape[0]
+    hd = q.shape[1] // num_heads
+    qh = q.view(Lq, num_heads, hd).permute(1, 0, 2).unsqueeze(0)
+    kh = k.view(Lk, num_heads, hd).permute(1, 0, 2).unsqueeze(0)
+    vh = v.view(Lk, num_heads, hd).permute(1, 0, 2).unsqueeze(0)
+    o = F.scaled_dot_product_attention(qh, kh, vh)
+    return o.squeeze(0).permute(1, 0, 2).reshape(Lq, num_heads * hd)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# one block
+# ------------------------------------------------------------------------------------------------------------
+class WanBlockQ:
+    """Integer runtime of WanAttentionBlock.forward (wan/modules/model.py:293-370)."""
+
+    def __init__(self, cfg: WanConfig, w: dict, a_bits=8):
+        self.cfg, self.a_bits = cfg, a_bits
+        self.w_qkv = w["self_attn.qkv"]
+        self.w_o = w["self_attn.o"]
+        self.w_cq, self.w_ckv, self.w_co = w["cross_attn.q"], w["cross_attn.kv"], w["cross_attn.o"]
+        self.w_f0, self.w_f2 = w["ffn.0"], w["ffn.2"]
+        self.norm_q, self.norm_k = w["self_attn.norm_q.weight"], w["self_attn.norm_k.weight"]
+        self.cnorm_q, self.cnorm_k = w["cross_attn.norm_q.weight"], w["cross_attn.norm_k.weight"]
+        self.norm3_w, self.norm3_b = w.get("norm3.weight"), w.get("norm3.bias")
+        self.modulation = w["modulation"].reshape(6, -1).float()
+        self.attention_fn = None          # set by the sequence-parallel wrapper / int8 attention
+
+    @staticmethod
+    def from_fp_params(cfg: WanConfig, p: dict, w_bits=8, w_sym=False, w_bits_by_layer=None):
+        """p: fp32 tensors keyed like oracle.fakequant_oracle.make_block_params (same names as the module tree)."""
+        w_bits_by_layer = w_bits_by_layer or {}
+
+        def q(name):
+            return QWeight.from_fp(p[name + ".weight"], p.get(name + ".bias"), w_bits_by_layer.get(name, w_bits), w_sym)
+
+        w = {
+            "self_attn.qkv": QWeight.cat([q("self_attn.q"), q("self_attn.k"), q("self_attn.v")]),
+            "self_attn.o": q("self_attn.o"),
+            "cross_attn.q": q("cross_attn.q"),
+            "cross_attn.kv": QWeight.cat([q("cross_attn.k"), q("cross_attn.v")]),
+            "cross_attn.o": q("cross_attn.o"),
+            "ffn.0": q("ffn.0"), "ffn.2": q("ffn.2"),
+        }
+        for k in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight",
+                  "cross_attn.norm_k.weight", "norm3.weight", "norm3.bias", "modulation"):
+            if k in p:
+                w[k] = p[k].detach().float().cuda().contiguous()
+        return WanBlockQ(cfg, w)
+
+    @staticmethod
+    def random(cfg: WanConfig, generator=None, w_bits=8, ffn_bits=None):
+        D, Fd = cfg.dim, cfg.ffn_dim
+        fb = ffn_bits or w_bits
+        dev = "cuda"
+        w = {
+            "self_attn.qkv": QWeight.random(3 * D, D, w_bits, dev, generator),
+            "self_attn.o": QWeight.random(D, D, w_bits, dev, generator),
+            "cross_attn.q": QWeight.random(D, D, w_bits, dev, generator),
+            "cross_attn.kv": QWeight.random(2 * D, D, w_bits, dev, generator),
+            "cross_attn.o": QWeight.random(D, D, w_bits, dev, generator),
+            "ffn.0": QWeight.random(Fd, D, fb, dev, generator),
+            "ffn.2": QWeight.random(D, Fd, fb, dev, generator),
+            "modulation": torch.randn(6, D, device=dev, generator=generator) / D ** 0.5,
+            "norm3.weight": torch.ones(D, device=dev), "norm3.bias": torch.zeros(D, device=dev),
+        }
+        for k in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight", "cross_attn.norm_k.weight"):
+            w[k] = torch.ones(D, device=dev)
+        return WanBlockQ(cfg, w)
+
+    # ---- forward ------------------------------------------------------------------------------------------
+    def context_kv(self, context):
+        """cross-attention K,V of the (rank-replicated) text context [T, D] — token-local, once per block."""
+        cfg = self.cfg
+        qc, dc, _, rc = b200q.quant_rows(context, self.a_bits, True, True)
+        kv = qlinear(qc, dc, rc, self.w_ckv)                                   # [T, 2D] bf16
+        k = rmsnorm_rope(kv[:, :cfg.dim], self.cnorm_k, cfg.eps)
+        return k, kv[:, cfg.dim:]
+
+    def forward(self, x, e0, context, cos, sin, attention=None):
+        """x [L, D] fp32 (updated in place and returned), e0 [6, D] fp32, context [T, D] fp32/bf16."""
+        cfg = self.cfg
+        D, H = cfg.dim, cfg.num_heads
+        e = self.modulation + e0                                                # model.py:322-324 (fp32)
+        attention = attention or self.attention_fn or (lambda q, k, v: sdpa(q, k, v, H))
+
+        # ---- self attention (model.py:327-337 with xdit_context_parallel.py:163-165 semantics) ----
+        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, shift=e[0], scale=e[1], n_bits=self.a_bits)
+        qkv = qlinear(qa, da, rs, self.w_qkv)                                   # [L, 3D] bf16
+        q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H)
+        k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H)
+        a = attention(q, k, qkv[:, 2 * D:])
+        qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
+        qlinear(qa, da, rs, self.w_o, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[2])
+
+        # ---- cross attention (model.py:180-200, 351-353) ----
+        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, ln_w=self.norm3_w, ln_b=self.norm3_b, n_bits=self.a_bits)
+        q = rmsnorm_rope(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps)
+        ck, cv = self.context_kv(context)
+        a = sdpa(q, ck, cv, H)
+        qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
+        qlinear(qa, da, rs, self.w_co, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=None)
+
+        # ---- ffn (model.py:286-288, 359-362) ----
+        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, shift=e[3], scale=e[4], n_bits=self.a_bits)
+        h = qlinear(qa, da, rs, self.w_f0, epilogue=b200q.EPI_GELU_TANH)       # [L, F] bf16
+        qa, da, _, rs = b200q.quant_rows(h, self.a_bits, True, True)
+        qlinear(qa, da, rs, self.w_f2, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[5])
+        return x
+
+    def gemm_ops(self, L, T):
+        D, Fd = self.cfg.dim, self.cfg.ffn_dim
+        return 2 * (L * D * 3 * D + L * D * D + L * D * D + T * D * 2 * D + L * D * D + 2 * L * D * Fd)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# full DiT
+# ------------------------------------------------------------------------------------------------------------
+def sinusoidal_embedding_1d(dim, position):
+    """model.py:17-28 (float64)."""
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
+
+
+class WanDiTQ:
+    """WanModel.forward (model.py:539-631) with the quantized blocks above.  Embeddings, time/text MLPs and the head
+    stay FP, as the reference's `remain_fp_regex` keeps them (quant_configs/config.yaml:9)."""
+
+    def __init__(self, cfg: WanConfig, blocks, fp: dict, sp=None):
+        self.cfg, self.blocks, self.fp, self.sp = cfg, blocks, fp, sp
+
+    @staticmethod
+    def random(cfg: WanConfig, seed=0, w_bits=8, ffn_bits=None, sp=None, num_layers=None):
+        """Random-init weights of the named architecture (no checkpoints offline): blocks as codes+scales on device,
+        FP parts with WanModel.init_weights statistics (model.py:658-680)."""
+        g = torch.Generator(device="cuda").manual_seed(seed)
+        D = cfg.dim
+        n = num_layers or cfg.num_layers
+        blocks = [WanBlockQ.random(cfg, g, w_bits, ffn_bits) for _ in range(n)]
+
+        def lin(o, i, std=None):
+            a = math.sqrt(6.0 / (i + o))
+            w = (torch.rand(o, i, device="cuda", generator=g) * 2 - 1) * a if std is None else \
+                torch.randn(o, i, device="cuda", generator=g) * std
+            return w.to(torch.bfloat16), torch.zeros(o, device="cuda", dtype=torch.bfloat16)
+
+        pdim = cfg.in_dim * math.prod(cfg.patch_size)
+        fp = {
+            "patch": lin(D, pdim),
+            "text0": lin(D, cfg.text_dim, 0.02), "text2": lin(D, D, 0.02),
+            "time0": lin(D, cfg.freq_dim, 0.02), "time2": lin(D, D, 0.02), "timeproj": lin(6 * D, D),
+            "head": (torch.randn(cfg.out_dim * math.prod(cfg.patch_size), D, device="cuda", generator=g).mul(0.02).to(torch.bfloat16),
+                     torch.zeros(cfg.out_dim * math.prod(cfg.patch_size), device="cuda", dtype=torch.bfloat16)),
+            "head_mod": torch.randn(2, D, device="cuda", generator=g) / D ** 0.5,
+        }
+        return WanDiTQ(cfg, blocks, fp, sp)
+
+    def embed(self, latent, t, context):
+        """patch embedding (Conv3d with stride == kernel == a linear on patches), time MLP (fp32), text MLP."""
+        cfg, fp = self.cfg, self.fp
+        C, Fr, Hh, Ww = latent.shape
+        pt, ph, pw = cfg.patch_size
+        grid = (Fr // pt, Hh // ph, Ww // pw)
+        patches = latent.view(C, grid[0], pt, grid[1], ph, grid[2], pw).permute(1, 3, 5, 0, 2, 4, 6).reshape(
+            grid[0] * grid[1] * grid[2], C * pt * ph * pw)
+        x = F.linear(patches.to(torch.bfloat16), *fp["patch"]).float()             # residual stream is fp32
+        te = sinusoidal_embedding_1d(cfg.freq_dim, t).float().to(x.device)
+        e = F.linear(F.silu(F.linear(te, fp["time0"][0].float(), fp["time0"][1].float())), fp["time2"][0].float(),
+                     fp["time2"][1].float())
+        e0 = F.linear(F.silu(e), fp["timeproj"][0].float(), fp["timeproj"][1].float()).view(6, cfg.dim)
+        ctx = torch.zeros(cfg.text_len, cfg.text_dim, device=x.device, dtype=torch.bfloat16)
+        ctx[:context.shape[0]] = context.to(torch.bfloat16)
+        ctx = F.linear(F.gelu(F.linear(ctx, *fp["text0"]), approximate="tanh"), *fp["text2"])
+        return x, e, e0, ctx, grid
+
+    def head(self, x, e):
+        cfg, fp = self.cfg, self.fp
+        m = fp["head_mod"] + e                                                       # [2, D]
+        _, _, _, y = b200q.ln_mod_quant(x, cfg.eps, shift=m[0], scale=m[1], quant=False, y_dtype=torch.bfloat16)
+        return F.linear(y, *fp["head"]).float()
+
+    def unpatchify(self, y, grid):
+        cfg = self.cfg
+        c = cfg.out_dim
+        u = y.view(*grid, *cfg.patch_size, c)
+        u = torch.einsum("fhwpqrc->cfphqwr", u)
+        return u.reshape(c, *[i * j for i, j in zip(grid, cfg.patch_size)])
+
+    @torch.no_grad()
+    def forward(self, latent, t, context):
+        """latent [C, F, H, W], t [1], context [T<=512, text_dim] -> denoised latent [C, F, H, W] fp32."""
+        x, e, e0, ctx, grid = self.embed(latent, t, context)
+        L = x.shape[0]
+        sp = self.sp
+        if sp is not None and sp.world_size > 1:
+            x, off, Lr = sp.shard_tokens(x)                        # xdit_context_parallel.py:131-133
+        else:
+            off, Lr = 0, L
+        cos, sin = rope_table(self.cfg.head_dim, grid, x.device, off, Lr)
+        if sp is not None and sp.world_size > 1 and cos.shape[0] < x.shape[0]:   # padded tail tokens: identity rotation
+            pad = x.shape[0] - cos.shape[0]
+            cos = torch.cat([cos, torch.ones(pad, cos.shape[1], device=cos.device)])
+            sin = torch.cat([sin, torch.zeros(pad, sin.shape[1], device=sin.device)])
+        attn = (lambda q, k, v: sp.attention(q, k, v, self.cfg.num_heads)) if (sp is not None and sp.world_size > 1) else None
+        x = x.contiguous()
+        for blk in self.blocks:
+            blk.forward(x, e0, ctx, cos, sin, attention=attn)
+        y = self.head(x, e[0])
+        if sp is not None and sp.world_size > 1:
+            y = sp.gather_tokens(y, L)                             # xdit_context_parallel.py:142
+        return self.unpatchify(y, grid)
+
+    def gemm_ops(self, L):
+        return sum(b.gemm_ops(L, self.cfg.text_len) for b in self.blocks)

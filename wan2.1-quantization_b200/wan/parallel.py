@@ -1,0 +1,147 @@
+"""Sequence parallelism for the quantized DiT step: one process per GPU, NCCL over NVLink/NVSwitch.
+
+Replaces xfuser/yunchang's Ulysses path (ViDiT-Q/examples/Wan2.1/wan/distributed/xdit_context_parallel.py:66-192;
+xfuser hybrid/attn_layer.py:160-206 = 4 separate c10d all-to-alls per block) with one packed q|k|v exchange and one
+output exchange per attention, issued as grouped NCCL send/recv (`batch_isend_irecv`), no xfuser dependency.
+
+Every stage of a block except attention is token-local (per-token activation scales make the quantized linears
+exactly invariant to sequence sharding), so ranks own contiguous token chunks
+`x[r*L/P:(r+1)*L/P]` (xdit_context_parallel.py:131-133) with weights replicated.
+
+Head/query decomposition.  P = Pu * Pr with Pu = gcd-style largest divisor of P that divides the head count:
+  rank r = h*Pu + g   owns head-group g (H/Pu heads) for the query range of replica h (the tokens of ranks
+  h*Pu .. h*Pu+Pu-1) against ALL keys/values.
+Pr == 1 is plain Ulysses (12-head Wan-1.3B at P in {1,2,4}; 40-head 14B at P in {2,4,8}).  Pr == 2 covers the
+1.3B model on 8 GPUs, where 12 heads do not divide by 8 (the reference refuses that case,
+quant_generate.py:451-452): Ulysses-4 x 2-way key/value replication — K,V of a head group go to both replicas.
+NVSwitch gives every pair full bandwidth, so the extra K/V copy costs bytes, not hops.
+"""
+from __future__ import annotations
+
+import math
+
+import torch
+import torch.distributed as dist
+
+
+def _largest_head_divisor(world, heads):
+    best = 1
+    for pu in range(1, world + 1):
+        if world % pu == 0 and heads % pu == 0:
+            best = pu
+    return best
+
+
+class SequenceParallel:
+    def __init__(self, group=None, attention_core=None):
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.attention_core = attention_core          # (q,k,v,num_heads)->o ; default library SDPA
+        self.bytes_sent = 0                            # per-rank payload counter (bench/DESIGN accounting)
+
+    # ---- token sharding ------------------------------------------------------------------------------------
+    def chunk(self, L):
+        P = self.world_size
+        if L % P != 0:
+            raise ValueError(f"sequence length {L} must divide by the sequence-parallel size {P} "
+                             "(the reference pads to a multiple of sp_size, text2video.py:170-172)")
+        return L // P
+
+    def shard_tokens(self, x):
+        Lr = self.chunk(x.shape[0])
+        off = self.rank * Lr
+        return x[off:off + Lr], off, Lr
+
+    def gather_tokens(self, y, L):
+        """all_gather along tokens (xdit_context_parallel.py:142)."""
+        y = y.contiguous()
+        out = torch.empty((self.world_size * y.shape[0],) + tuple(y.shape[1:]), dtype=y.dtype, device=y.device)
+        dist.all_gather_into_tensor(out, y, group=self.group)
+        return out[:L]
+
+    # ---- attention exchange ------------------------------------------------------------------------------------
+    def plan(self, num_heads):
+        P = self.world_size
+        Pu = _largest_head_divisor(P, num_heads)
+        Pr = P // Pu
+        return Pu, Pr, self.rank % Pu, self.rank // Pu
+
+    def _exchange(self, sends, recvs):
+        """grouped point-to-point = NCCL all-to-all with per-peer sizes; self-copy done locally."""
+        ops = []
+        for peer in range(self.world_size):
+            s, r = sends[peer], recvs[peer]
+            if peer == self.rank:
+                if r is not None and s is not None:
+                    r.copy_(s)
+                continue
+            if r is not None and r.numel() > 0:
+                ops.append(dist.P2POp(dist.irecv, r, self._global(peer), group=self.group))
+            if s is not None and s.numel() > 0:
+                ops.append(dist.P2POp(dist.isend, s, self._global(peer), group=self.group))
+                self.bytes_sent += s.numel() * s.element_size()
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+
+    def _global(self, peer):
+        return peer if self.group is None else dist.get_global_rank(self.group, peer)
+
+    def attention(self, q, k, v, num_heads):
+        """q,k,v: this rank's tokens, all heads, [Lr, H*hd] -> attention output [Lr, H*hd] for the same tokens."""
+        from . import model as M                       # late import: model imports nothing from here
+        P = self.world_size
+        core = self.attention_core or M.sdpa
+        if P == 1:
+            return core(q, k, v, num_heads)
+        Lr, D = q.shape
+        hd = D // num_heads
+        Pu, Pr, g, h = self.plan(num_heads)
+        Hg = num_heads // Pu
+        W = Hg * hd
+        # pack per destination: [k | v | (q)] for the destination's head group
+        sends, recvs = [None] * P, [None] * P
+        for dst in range(P):
+            gd, hdst = dst % Pu, dst // Pu
+            cols = slice(gd * W, (gd + 1) * W)
+            parts = [k[:, cols], v[:, cols]]
+            if hdst == h:                              # my tokens' queries are served by replica h
+                parts.append(q[:, cols])
+            sends[dst] = torch.stack(parts, 0).contiguous()
+        for src in range(P):
+            n = 3 if (src // Pu) == h else 2
+            recvs[src] = torch.empty((n, Lr, W), dtype=q.dtype, device=q.device)
+        self._exchange(sends, recvs)
+        K = torch.cat([recvs[s][0] for s in range(P)], 0)                        # [L, W]
+        V = torch.cat([recvs[s][1] for s in range(P)], 0)
+        q_src = [s for s in range(P) if s // Pu == h]
+        Q = torch.cat([recvs[s][2] for s in q_src], 0)                           # [L/Pr, W]
+        O = core(Q, K, V, Hg)                                                    # [L/Pr, W]
+        # return each token owner its rows of my head group
+        sends, recvs = [None] * P, [None] * P
+        for i, s in enumerate(q_src):
+            sends[s] = O[i * Lr:(i + 1) * Lr].contiguous()
+        for gsrc in range(Pu):                          # ranks (gsrc, h) computed my tokens
+            recvs[h * Pu + gsrc] = torch.empty((Lr, W), dtype=q.dtype, device=q.device)
+        self._exchange(sends, recvs)
+        return torch.cat([recvs[h * Pu + gsrc] for gsrc in range(Pu)], 1)        # [Lr, H*hd]
+
+    # ---- calibration ---------------------------------------------------------------------------------------------
+    def allreduce_max(self, flat_stats):
+        """Merge per-rank running abs-max over the sequence-sharded tokens: ONE allreduce(MAX) on the flat fp32
+        buffer instead of pickled all_gather_object + cat + max (get_calib_data_wanx.py:443-468, ptq_wanx.py:336)."""
+        if self.world_size > 1:
+            dist.all_reduce(flat_stats, op=dist.ReduceOp.MAX, group=self.group)
+        return flat_stats
+
+
+def exchange_bytes_per_rank(L, D, P, num_heads, elem=2):
+    """Algorithmic payload one rank sends per attention (q|k|v out + o back), for the roofline notes."""
+    Pu = _largest_head_divisor(P, num_heads)
+    Pr = P // Pu
+    Lr, W = L // P, D // Pu
+    kv = 2 * Lr * W * elem * (P - 1)
+    q = Lr * W * elem * (Pu - 1)
+    o = Lr * W * elem * (Pu - 1)
+    return kv + q + o, Pu, Pr
