@@ -131,16 +131,20 @@ B200Q_API int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, i
                     int epilogue, const float* residual, int64_t ldr, const float* gate,
                     b200q_stream_t stream);
 
-/* codes int8 [N,K] in [-8,7] -> packed uint8 [N,K/2]: byte j of row n holds code[n,2j] in
- * bits 0-3 and code[n,2j+1] in bits 4-7 (two's-complement nibbles). K must be even. */
+/* codes int8 [N,K] in [-8,7] -> packed uint8 [N, ceil(K/8)*4].  Format (consumed by b200q_gemm_w4a8's in-smem
+ * unpacker): K is split in groups of 8 codes; byte i (i=0..3) of the group's 32-bit word holds (code[i]+8) in bits 0-3
+ * and (code[4+i]+8) in bits 4-7.  Nibbles are unsigned (the +8 bias is folded into the GEMM's zero-point term, the
+ * algebra of the reference's QServe kernel, w4a8_per_channel_gemm_cuda_qserve.cu:290-297,585-586), so the unpack
+ * is one AND and one SHIFT+AND per four codes.  ldp (bytes) must be a multiple of 4; use a multiple of 16 for the GEMM. */
 B200Q_API int b200q_pack_w4(const int8_t* codes, int64_t ld, int64_t N, int64_t K,
                   uint8_t* packed, int64_t ldp, b200q_stream_t stream);
 
 /* Same contract as b200q_gemm_w8a8 with 4-bit weights packed by b200q_pack_w4
  * (replaces qgemm.w4a8_of16_nobias_weight_asym_qserve,
  *  kernels/csrc/qgemm/w4a8/w4a8_per_channel_gemm_cuda_qserve.cu:304-656).
- * qw4 [N,K/2] uint8 (ldw4 bytes, multiple of 16); nibbles are sign-extended to int8 in
- * shared memory before the MMA. */
+ * qw4 [N, ceil(K/8)*4] uint8 (ldw4 bytes, multiple of 16).  The packed tile travels by TMA; four converter warps expand
+ * it to an int8 SWIZZLE_128B tile in shared memory before the MMA.  rowsum_a is REQUIRED (nibble bias); with
+ * out_dtype B200Q_I32 the raw accumulators are sum_k qa*(code+8). */
 B200Q_API int b200q_gemm_w4a8(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4,
                     const float* delta_a, const float* delta_w, const float* zp_w,
                     const int32_t* rowsum_a, const void* bias, int bias_dtype,
@@ -170,6 +174,15 @@ B200Q_API int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int64
 B200Q_API int b200q_gate_residual(const void* y, int y_dtype, int64_t ldy, const float* gate,
                         const float* residual, int64_t ldr, float* out, int64_t ldo,
                         int64_t rows, int64_t cols, b200q_stream_t stream);
+
+/* y = RMSNorm_D(x) (fp32 statistics, cast back to x's dtype, * weight[cols]) then, if cos/sin are given, the 3-axis RoPE
+ * rotation of adjacent channel pairs of every head: (a,b) -> (a*cos - b*sin, a*sin + b*cos) with cos/sin
+ * [rows, head_dim/2] fp32 (host-built in float64 from the token's (f,h,w) position, rank-offset under sequence
+ * parallelism).  x bf16|fp16 [rows, cols] -> out bf16 [rows, cols].  Replaces WanRMSNorm + rope_apply
+ * (wan/modules/model.py:43-89; xdit_context_parallel.py:25-63). */
+B200Q_API int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                       const float* weight, float eps, const float* cos_t, const float* sin_t, int head_dim,
+                       void* out, int64_t ldo, b200q_stream_t stream);
 
 /* ---- (c) quantized attention ------------------------------------------------------------
  * See DESIGN.md §attention; declared in later sections of this header as they land. */

@@ -76,3 +76,22 @@ def test_calibration_collector(dev):
     sd = col.state_dict()
     assert torch.equal(sd["0"].max(dim=0)[0], O.calib_merge(ref0))
     assert torch.equal(sd["2"].max(dim=0)[0], O.calib_merge(ref1))
+
+
+@pytest.mark.parametrize("L,heads,hd,grid", [(96, 2, 128, (2, 6, 8)), (60, 3, 64, (3, 4, 5))])
+def test_rmsnorm_rope_kernel(dev, L, heads, hd, grid):
+    """Fused RMSNorm(full dim)+RoPE vs the oracle restatement of model.py:43-89 (float64 complex RoPE)."""
+    D = heads * hd
+    g = torch.Generator().manual_seed(L)
+    x = (torch.randn(L, 3 * D, generator=g) * 2).to(torch.bfloat16)
+    w = torch.rand(D, generator=g) + 0.5
+    xs = x[:, D:2 * D]                                             # strided slice, like k inside the fused qkv output
+    cos, sin = M.rope_table(hd, grid, dev)
+    out = b200q.rmsnorm_rope(xs.to(dev) if False else x.to(dev)[:, D:2 * D], w.to(dev), 1e-6, cos, sin, hd).cpu().float()
+    ref = O.rms_norm(xs, w, 1e-6)                                  # bf16 in -> fp32 (type_as(x) * fp32 weight)
+    ref = O.rope_apply(ref.view(L, heads, hd), grid, O.wan_freqs(hd)).reshape(L, D)
+    assert float((out - ref).abs().max()) <= 2e-2 * float(ref.abs().max())     # bf16 output rounding
+    c = float((out.double().flatten() @ ref.double().flatten()) / (out.double().norm() * ref.double().norm()))
+    assert c >= 0.99999
+    out2 = b200q.rmsnorm_rope(x.to(dev)[:, :D], w.to(dev), 1e-6).cpu().float()
+    assert float((out2 - O.rms_norm(x[:, :D], w, 1e-6)).abs().max()) <= 2e-2 * float(out2.abs().max())

@@ -142,3 +142,65 @@ def test_bad_arguments_raise(dev):
         b200q.gemm_w8a8(qa, qw, out_dtype=torch.int32)
     with pytest.raises(b200q.B200QError):
         b200q.quant_rows(torch.zeros(4, 4), 8, True, True)     # CPU tensor: no fallback
+
+
+# ---- W4A8 ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(256, 512, 256), (300, 520, 1536), (64, 256, 8960), (130, 40, 144), (77, 264, 208)])
+@pytest.mark.parametrize("with_zp", [True, False])
+def test_w4a8_gemm(dev, M, N, K, with_zp):
+    g = torch.Generator().manual_seed(M + N + K)
+    qa = _codes(M, K, 21)
+    qw = _codes(N, K, 22, -8, 7)
+    da = torch.rand(M, generator=g) * 0.01 + 0.005
+    dw = torch.rand(N, generator=g) * 0.1 + 0.1
+    zp = torch.randint(-3, 4, (N,), generator=g).float() if with_zp else None
+    bias = torch.randn(N, generator=g)
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+    acc = O.int_accumulators(qa, qw).double()
+    if with_zp:
+        acc = acc + zp.double()[None, :] * rs.double()[:, None]
+    ref = da.double()[:, None] * dw.double()[None, :] * acc + bias.double()[None, :]
+    packed = b200q.pack_w4(qw.to(dev))
+    out = b200q.gemm_w4a8(qa.to(dev), packed, K, da.to(dev), dw.to(dev), None if zp is None else zp.to(dev), rs.to(dev),
+                          bias.to(dev), out_dtype=torch.float32)
+    rel = float(((out.cpu().double() - ref).abs() / (ref.abs() + 1.0)).max())
+    assert rel <= 2e-5, rel          # exact integer accumulation: only the fp32 epilogue rounds
+
+
+def test_w4a8_quantized_linear_golden(dev, golden_dir):
+    """W4 asym weights / A8 sym activations end to end vs the imported reference QuantizedLinear (fp32 fake-quant)."""
+    rec = torch.load(os.path.join(golden_dir, "quantized_linear.pt"))["w4a8"]
+    x = rec["x"].reshape(-1, rec["x"].shape[-1]).to(dev)
+    qw, dw, zw, _ = b200q.quant_rows(rec["weight"].to(dev), 4, False, False, want_rowsum=False)
+    assert torch.equal(dw.cpu(), rec["w_delta"].flatten()) and torch.equal(zw.cpu(), rec["w_zero_point"].flatten())
+    assert int(qw.min()) >= -8 and int(qw.max()) <= 7
+    qa, da, _, rs = b200q.quant_rows(x, 8, True, True)
+    K = x.shape[1]
+    Kp = (K + 15) // 16 * 16
+    qa_p = torch.zeros(qa.shape[0], Kp, dtype=torch.int8, device=dev); qa_p[:, :K] = qa
+    y = b200q.gemm_w4a8(qa_p[:, :K], b200q.pack_w4(qw), K, da, dw, zw, rs, rec["bias"].to(dev), out_dtype=torch.float32)
+    ref = rec["y"].reshape(-1, rec["y"].shape[-1])
+    err = (y.cpu() - ref).abs() / (ref.abs() + 1.0)
+    assert float(err.max()) <= 2e-5, float(err.max())
+
+
+def test_w4a8_gelu_and_gate_epilogues(dev):
+    M, N, K = 200, 512, 384
+    g = torch.Generator().manual_seed(5)
+    qa, qw = _codes(M, K, 31), _codes(N, K, 32, -8, 7)
+    da = torch.rand(M, generator=g) * 2e-3 + 1e-4
+    dw = torch.rand(N, generator=g) * 1e-2 + 1e-3
+    zp = torch.randint(-2, 3, (N,), generator=g).float()
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+    y = da[:, None].double() * dw[None, :].double() * (O.int_accumulators(qa, qw).double() + zp.double()[None, :] * rs.double()[:, None])
+    packed = b200q.pack_w4(qw.to(dev))
+    out = b200q.gemm_w4a8(qa.to(dev), packed, K, da.to(dev), dw.to(dev), zp.to(dev), rs.to(dev), None,
+                          out_dtype=torch.bfloat16, epilogue=b200q.EPI_GELU_TANH)
+    ref = torch.nn.functional.gelu(y.float(), approximate="tanh")
+    assert _cos(out.cpu().float(), ref) >= 0.9999
+    res = torch.randn(M, N, generator=g)
+    gate = torch.randn(N, generator=g)
+    x = res.clone().to(dev)
+    b200q.gemm_w4a8(qa.to(dev), packed, K, da.to(dev), dw.to(dev), zp.to(dev), rs.to(dev), None,
+                    epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=gate.to(dev))
+    assert float((x.cpu().double() - (res.double() + y * gate.double())).abs().max()) <= 1e-4

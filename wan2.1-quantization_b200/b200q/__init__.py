@@ -54,6 +54,8 @@ _SIGNATURES = {
     "b200q_ln_mod_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
                                    c_void_p, c_int, c_int64, c_void_p]),
+    "b200q_rmsnorm_rope": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
+                                   c_int, c_void_p, c_int64, c_void_p]),
     "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                     c_int64, c_int64, c_void_p]),
 }
@@ -230,8 +232,11 @@ def pack_w4(codes):
     """int8 codes in [-8,7], [N,K] -> packed uint8 [N, ceil(K/8)*4] (format: csrc/w4.cu)."""
     codes = _rows2d(codes, "pack_w4")
     N, K = codes.shape
-    packed = torch.empty((N, ((K + 7) // 8) * 4), dtype=torch.uint8, device=codes.device)
-    rc = load().b200q_pack_w4(_ptr(codes), _ld(codes), N, K, _ptr(packed), _ld(packed), _stream())
+    nbytes = ((K + 7) // 8) * 4
+    pitch = (nbytes + 15) // 16 * 16                         # TMA global stride: multiple of 16 bytes
+    buf = torch.zeros((N, pitch), dtype=torch.uint8, device=codes.device)
+    packed = buf[:, :nbytes]
+    rc = load().b200q_pack_w4(_ptr(codes), _ld(codes), N, K, _ptr(packed), pitch, _stream())
     _check(rc, "b200q_pack_w4")
     return packed
 
@@ -240,6 +245,8 @@ def gemm_w4a8(qa, qw4, K, delta_a=None, delta_w=None, zp_w=None, rowsum_a=None, 
               out_dtype=torch.bfloat16, epilogue=EPI_NONE, residual=None, gate=None, out=None):
     """Same contract as gemm_w8a8 with weights packed by pack_w4 (rowsum_a is always required:
     the unsigned-nibble bias is folded through the zero-point term)."""
+    if out_dtype == torch.int32:
+        raise B200QError("gemm_w4a8: raw accumulators carry the +8 nibble bias; request a dequantised output")
     return _gemm("b200q_gemm_w4a8", qa, qw4, qw4.shape[0], K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype,
                  epilogue, residual, gate, out)
 
@@ -290,4 +297,18 @@ def gate_residual(y, residual, gate=None, out=None):
     rc = load().b200q_gate_residual(_ptr(y), _DTYPE[y.dtype], _ld(y), _ptr(gate), _ptr(residual), _ld(residual),
                                     _ptr(out), _ld(out), rows, cols, _stream())
     _check(rc, "b200q_gate_residual")
+    return out
+
+
+def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0):
+    """RMSNorm over the full dim (+ RoPE when cos/sin [rows, head_dim/2] are given); x bf16/fp16 [rows, cols] (may be a
+    strided column slice) -> bf16 [rows, cols]."""
+    _cuda(x, "rmsnorm_rope")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise B200QError("rmsnorm_rope: expected a row-major 2-D tensor")
+    rows, cols = x.shape
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    rc = load().b200q_rmsnorm_rope(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(weight), float(eps), _ptr(cos),
+                                   _ptr(sin), int(head_dim), _ptr(out), _ld(out), _stream())
+    _check(rc, "b200q_rmsnorm_rope")
     return out

@@ -205,6 +205,109 @@ static int launch_ln(const LnArgs& a, cudaStream_t st) {
   return B200Q_OK;
 }
 
+// ---- RMSNorm over the full model dim + 3-axis RoPE --------------------------------------------
+// WanRMSNorm (wan/modules/model.py:73-89: fp32 statistics, result cast back to x's dtype, then * weight) followed by
+// rope_apply (model.py:43-70; the reference multiplies complex128 numbers per sample in a Python loop): adjacent
+// channel pairs (2i, 2i+1) of every head are rotated by the angle of the token's (frame, row, col) position, which the
+// host passes as fp32 cos/sin tables [rows, head_dim/2] computed in float64.  One read of q (or k), one bf16 write.
+struct RopeArgs {
+  const void* x;
+  int64_t rows, cols, ldx;
+  const float* weight;
+  float eps;
+  const float* cos_t;
+  const float* sin_t;
+  int head_dim;
+  void* out;
+  int64_t ldo;
+};
+
+template <typename T, int V, int THREADS>
+__global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a, const int warps_per_row) {
+  using VT = Vec16<T>;
+  constexpr int N = VT::N;            // 8 (bf16 / fp16)
+  __shared__ float s_buf[32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int rows_per_cta = (blockDim.x >> 5) / warps_per_row;
+  const int row_in_cta = warp / warps_per_row;
+  const int w0 = row_in_cta * warps_per_row;
+  const int wr = warp - w0;
+  const int64_t row = (int64_t)blockIdx.x * rows_per_cta + row_in_cta;
+  const bool row_ok = row < a.rows;
+  const int tpr = warps_per_row * 32;
+  const int t = wr * 32 + lane;
+  const int kv = (int)(a.cols / N);
+  const T* xrow = reinterpret_cast<const T*>(a.x) + (row_ok ? row : 0) * a.ldx;
+  float f[V][N];
+  float ss = 0.f;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int j = v * tpr + t;
+    const uint4 raw = (row_ok && j < kv) ? ldg_stream16(xrow + (int64_t)j * N) : make_uint4(0, 0, 0, 0);
+    VT::unpack(raw, f[v]);
+#pragma unroll
+    for (int i = 0; i < N; ++i) ss += f[v][i] * f[v][i];
+  }
+  const float ms = row_reduce_sum(ss, s_buf, warp, lane, w0, warps_per_row) / (float)a.cols;
+  const float rstd = __frsqrt_rn(ms + a.eps);
+  const int half = a.head_dim >> 1;
+#pragma unroll
+  for (int v = 0; v < V; ++v) {
+    const int j = v * tpr + t;
+    if (!(row_ok && j < kv)) continue;
+    const int c0 = j * N;
+    float y[N];
+#pragma unroll
+    for (int h = 0; h < N / 4; ++h) {
+      const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.weight + c0 + 4 * h));
+      const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) y[4 * h + i] = to_f32(from_f32<T>(f[v][4 * h + i] * rstd)) * wv[i];   // .type_as(x) * weight
+    }
+    if (a.cos_t != nullptr) {
+      const int p0 = (c0 % a.head_dim) >> 1;                 // first pair index inside the head (multiple of 4)
+      const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.cos_t + row * half + p0));
+      const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.sin_t + row * half + p0));
+      const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float re = y[2 * i], im = y[2 * i + 1];
+        y[2 * i] = re * cv[i] - im * sv[i];
+        y[2 * i + 1] = re * sv[i] + im * cv[i];
+      }
+    }
+    __nv_bfloat162 o[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+    stg_stream16(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + c0, *reinterpret_cast<uint4*>(o));
+  }
+}
+
+template <typename T>
+static int launch_rope(const RopeArgs& a, cudaStream_t st) {
+  constexpr int N = Vec16<T>::N;
+  const int kv = (int)(a.cols / N);
+  int W = 1;
+  while (W < 8 && (kv + 32 * W - 1) / (32 * W) > 3) W *= 2;
+  int threads = 256;
+  if ((kv + 32 * W - 1) / (32 * W) > 8) { W = 32; threads = 1024; }
+  const int V = (kv + 32 * W - 1) / (32 * W);
+  B200Q_REQUIRE(V <= 8, B200Q_ERR_UNSUPPORTED, "rmsnorm_rope: cols=%lld too large", (long long)a.cols);
+  const int rows_per_cta = (threads / 32) / W;
+  const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
+#define B200Q_RR(VV, TH) rmsnorm_rope_kernel<T, VV, TH><<<grid, TH, 0, st>>>(a, W)
+  if (threads == 1024) { if (V <= 4) B200Q_RR(4, 1024); else B200Q_RR(8, 1024); }
+  else if (V <= 1) B200Q_RR(1, 256);
+  else if (V <= 2) B200Q_RR(2, 256);
+  else if (V <= 3) B200Q_RR(3, 256);
+  else if (V <= 4) B200Q_RR(4, 256);
+  else if (V <= 6) B200Q_RR(6, 256);
+  else B200Q_RR(8, 256);
+#undef B200Q_RR
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
 // ---- gate residual ---------------------------------------------------------------------------------------
 template <typename YT>
 __global__ void __launch_bounds__(256) gate_residual_kernel(const YT* __restrict__ y, int64_t ldy,
@@ -327,4 +430,27 @@ extern "C" int b200q_gate_residual(const void* y, int y_dtype, int64_t ldy, cons
   }
   set_error("gate_residual: bad y_dtype %d", y_dtype);
   return B200Q_ERR_BAD_ARG;
+}
+
+extern "C" int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, const float* weight,
+                                  float eps, const float* cos_t, const float* sin_t, int head_dim, void* out, int64_t ldo,
+                                  b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "rmsnorm_rope: negative shape");
+  if (rows == 0 || cols == 0) return B200Q_OK;
+  B200Q_REQUIRE(x && weight && out, B200Q_ERR_BAD_ARG, "rmsnorm_rope: null pointer");
+  B200Q_REQUIRE(x_dtype == B200Q_BF16 || x_dtype == B200Q_F16, B200Q_ERR_BAD_ARG, "rmsnorm_rope: x must be bf16 or fp16");
+  B200Q_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols && aligned(x, 16) &&
+                    aligned(out, 16) && aligned(weight, 16),
+                B200Q_ERR_UNSUPPORTED, "rmsnorm_rope: cols/ldx/ldo must be multiples of 8 and pointers 16-byte aligned");
+  B200Q_REQUIRE((cos_t == nullptr) == (sin_t == nullptr), B200Q_ERR_BAD_ARG, "rmsnorm_rope: cos and sin go together");
+  if (cos_t) {
+    B200Q_REQUIRE(head_dim > 0 && head_dim % 8 == 0 && cols % head_dim == 0 && aligned(cos_t, 16) && aligned(sin_t, 16),
+                  B200Q_ERR_BAD_ARG, "rmsnorm_rope: head_dim must be a multiple of 8 dividing cols; tables 16-byte aligned");
+  }
+  RopeArgs a{};
+  a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.weight = weight; a.eps = eps; a.cos_t = cos_t; a.sin_t = sin_t;
+  a.head_dim = head_dim > 0 ? head_dim : (int)cols; a.out = out; a.ldo = ldo;
+  if (x_dtype == B200Q_BF16) return launch_rope<__nv_bfloat16>(a, (cudaStream_t)stream);
+  return launch_rope<__half>(a, (cudaStream_t)stream);
 }

@@ -27,22 +27,34 @@ using namespace ptx;
 
 constexpr int BM = 128, BN = 256, BK = 128;        // BK in bytes == int8 elements: one 128B swizzle row
 constexpr int UMMA_K = 32;                         // kind::i8: 32 bytes of K per instruction
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK, STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int EPI_WARPS = 4;
+constexpr int A_BYTES = BM * BK, B_BYTES = BN * BK;
+constexpr int CTRL_WARPS = 4;                      // TMA producer, MMA issuer, TMEM allocator, spare
+constexpr int EPI_WARPS = 8;                       // 2 per TMEM lane quarter: each owns 32 rows x 128 columns of a tile
+constexpr int CVT_WARPS = 4;                       // W4A8 only: int4 -> int8 unpackers
+constexpr int UNPACK_BUFS = 2;
 constexpr int STAGING_BYTES = 32 * 128;            // one warp: 32 rows x 128 B (swizzled)
-constexpr int GEMM_THREADS = 256;
 constexpr int TMEM_COLS = 512;
 
+// W8A8: ring stage = A tile (16 KB) + B tile (32 KB).
+// W4A8: ring stage = A tile (16 KB) + PACKED B tile (256 rows x 64 B = 16 KB); the converter warps expand it into one
+//       of two 32 KB SWIZZLE_128B int8 tiles that the MMA reads.
+// The gate-residual epilogue (8 B/element of HBM traffic: memory-bound) trades one ring stage for a second staging
+// buffer per epilogue warp so the residual box of chunk u+1 is in flight while chunk u is processed.
+template <bool W4, int EPI>
 struct GemmSmem {
-  // offsets into dynamic smem (base aligned to 1024 B)
+  static constexpr int stages = (EPI == B200Q_EPI_GATE_RESIDUAL) ? 3 : 4;
+  static constexpr int staging_bufs = (EPI == B200Q_EPI_GATE_RESIDUAL) ? 2 : 1;
+  static constexpr int b_stage = W4 ? B_BYTES / 2 : B_BYTES;
+  static constexpr int stage = A_BYTES + b_stage;
   static constexpr int ring = 0;
-  static constexpr int staging = STAGES * STAGE_BYTES;                       // EPI_WARPS x 2 x 4 KB
-  static constexpr int colparams = staging + EPI_WARPS * 2 * STAGING_BYTES;   // dw[BN] f32, bias[BN] f32, zp[BN] i16
+  static constexpr int unpack = stages * stage;
+  static constexpr int staging = unpack + (W4 ? UNPACK_BUFS * B_BYTES : 0);
+  static constexpr int colparams = staging + EPI_WARPS * staging_bufs * STAGING_BYTES;   // dw[BN] f32, bias[BN] f32, zp[BN] i16
   static constexpr int barriers = colparams + BN * 4 + BN * 4 + BN * 2;
   static constexpr int total = barriers + 256;
+  static constexpr int threads = (CTRL_WARPS + EPI_WARPS + (W4 ? CVT_WARPS : 0)) * 32;
+  static_assert(total <= 232448, "dynamic smem budget (227 KB) exceeded");
 };
-static_assert(GemmSmem::total <= 232448, "dynamic smem budget (227 KB) exceeded");
 
 struct GemmParams {
   int M, N, K;
@@ -97,9 +109,9 @@ __device__ __forceinline__ uint4 pack_chunk(const float* y) {
 }
 
 // OutT = int32_t -> raw accumulators.  EPI: b200q_epilogue.
-template <typename OutT, int EPI>
-__global__ void __launch_bounds__(GEMM_THREADS, 1)
-gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+template <typename OutT, int EPI, bool W4>
+__global__ void __launch_bounds__(GemmSmem<W4, EPI>::threads, 1)
+gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                  const GemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];          // SWIZZLE_128B tiles need 1024-byte alignment
@@ -107,12 +119,17 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + GemmSmem::barriers);
+  using SM = GemmSmem<W4, EPI>;
+  constexpr int STAGE_BYTES = SM::stage;
+  constexpr int STAGES = SM::stages;
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::barriers);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
   uint64_t* res_bar = tmem_empty_bar + 2;                      // EPI_WARPS barriers: residual tile landed
-  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(res_bar + EPI_WARPS);
+  uint64_t* bready_bar = res_bar + EPI_WARPS;                  // W4: unpacked B tile ready (converter -> MMA)
+  uint64_t* bfree_bar = bready_bar + UNPACK_BUFS;              // W4: unpacked B tile consumed (MMA -> converter)
+  uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bfree_bar + UNPACK_BUFS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
@@ -120,7 +137,11 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
   const int num_kb = (p.K + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < STAGES; ++s) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], W4 ? 1 + CVT_WARPS : 1);        // W4: the packed tile is also released by the converters
+    }
+    for (int s = 0; s < UNPACK_BUFS; ++s) { mbar_init(&bready_bar[s], CVT_WARPS); mbar_init(&bfree_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
@@ -143,10 +164,10 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + GemmSmem::ring + stage * STAGE_BYTES;
+          uint8_t* sa = smem + SM::ring + stage * STAGE_BYTES;
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
           tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, &tm_b, &full_bar[stage], kb * BK, n0);
+          tma_load_2d(sa + A_BYTES, &tm_b, &full_bar[stage], W4 ? kb * (BK / 2) : kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -156,6 +177,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     if (lane == 0) {
       constexpr uint32_t idesc = make_i8_idesc(BM, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
+      int ub = 0; uint32_t uphase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);          // epilogue has drained this accumulator
@@ -163,10 +185,11 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         const uint32_t tmem_d = tmem_base + as * BN;
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (W4) mbar_wait(&bready_bar[ub], uphase);        // int4 tile expanded to int8 by the converter warps
           tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + GemmSmem::ring + stage * STAGE_BYTES);
+          const uint32_t sa = smem_u32(smem + SM::ring + stage * STAGE_BYTES);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(sa + A_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(W4 ? smem_u32(smem + SM::unpack + ub * B_BYTES) : sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance both descriptors by k*32 bytes inside the 128B swizzle row (address field is >>4)
@@ -174,24 +197,85 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                       (kb | k) != 0 ? 1u : 0u);
           }
           mma_commit(&empty_bar[stage]);                     // slot free once these MMAs have read it
+          if (W4) {
+            mma_commit(&bfree_bar[ub]);
+            if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
+          }
           if (kb == num_kb - 1) mma_commit(&tmem_full_bar[as]);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
-  } else if (warp >= 4) {
+  } else if (W4 && warp >= CTRL_WARPS + EPI_WARPS) {
+    // ===================== W4A8 converter: packed int4 (TMA, no swizzle) -> int8 SWIZZLE_128B tile =====================
+    // packed word (csrc/w4.cu): byte i = (code[i]+8) | (code[4+i]+8) << 4 for a group of 8 codes, so the low nibbles
+    // are 4 consecutive K codes and the high nibbles the next 4: two AND/SHIFT ops per output word, no sign extension
+    // (the +8 bias is folded into the zero-point term of the epilogue).
+    const int ct = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;
+    int stage = 0; uint32_t phase = 0; int ub = 0; uint32_t uphase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < num_kb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        mbar_wait(&bfree_bar[ub], uphase ^ 1);
+        const uint8_t* src = smem + SM::ring + stage * STAGE_BYTES + A_BYTES;     // [256 rows][64 B]
+        uint8_t* dst = smem + SM::unpack + ub * B_BYTES;                           // [256 rows][128 B] swizzled
+#pragma unroll
+        for (int i = 0; i < (BN * 4) / (CVT_WARPS * 32); ++i) {
+          const int ci = i * (CVT_WARPS * 32) + ct;       // 16-byte packed chunk index: row = ci/4, j = ci%4
+          const int r = ci >> 2, j = ci & 3;
+          const uint4 w = *reinterpret_cast<const uint4*>(src + ci * 16);
+          uint4 o0, o1;
+          o0.x = w.x & 0x0F0F0F0Fu; o0.y = (w.x >> 4) & 0x0F0F0F0Fu; o0.z = w.y & 0x0F0F0F0Fu; o0.w = (w.y >> 4) & 0x0F0F0F0Fu;
+          o1.x = w.z & 0x0F0F0F0Fu; o1.y = (w.z >> 4) & 0x0F0F0F0Fu; o1.z = w.w & 0x0F0F0F0Fu; o1.w = (w.w >> 4) & 0x0F0F0F0Fu;
+          uint8_t* row = dst + r * 128;
+          *reinterpret_cast<uint4*>(row + (((2 * j) ^ (r & 7)) << 4)) = o0;
+          *reinterpret_cast<uint4*>(row + (((2 * j + 1) ^ (r & 7)) << 4)) = o1;
+        }
+        fence_proxy_async_smem();                          // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) {
+          mbar_arrive(&bready_bar[ub]);
+          mbar_arrive(&empty_bar[stage]);                  // this warp is done reading the packed tile
+        }
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
+      }
+    }
+  } else if (warp >= CTRL_WARPS && warp < CTRL_WARPS + EPI_WARPS) {
     // ===================== epilogue =====================
-    const int ew = warp - 4;                                 // == warp % 4: TMEM lane quarter
-    const int etid = threadIdx.x - 128;
-    float* s_dw = reinterpret_cast<float*>(smem + GemmSmem::colparams);
+    const int ew = warp - CTRL_WARPS;
+    const int quarter = ew & 3;                              // TMEM lane quarter this warp may read (== warp % 4)
+    const int half = ew >> 2;                                // which 128-column half of the tile
+    const int etid = threadIdx.x - CTRL_WARPS * 32;
+    float* s_dw = reinterpret_cast<float*>(smem + SM::colparams);
     float* s_bias = s_dw + BN;
     int16_t* s_zp = reinterpret_cast<int16_t*>(s_bias + BN);
-    uint8_t* my_staging = smem + GemmSmem::staging + ew * 2 * STAGING_BYTES;
     constexpr int ELEMS = OutPack<OutT>::ELEMS;              // outputs per 16 B
     constexpr int CPS = 8 * ELEMS;                           // columns per 128B staging row / TMA store box
+    constexpr int CHUNKS = (BN / 2) / CPS;                   // store boxes per warp per tile (even)
+    constexpr int NBUF = SM::staging_bufs;
     constexpr bool RAW = std::is_same<OutT, int32_t>::value;
+    constexpr bool GATE = (EPI == B200Q_EPI_GATE_RESIDUAL);
+    uint8_t* my_staging = smem + SM::staging + ew * NBUF * STAGING_BYTES;
+    const int col_base = half * (BN / 2);
     uint32_t res_phase = 0;
-    int it = 0; int sbuf = 0;
+
+    // residual prefetch (GATE): box [32 rows x CPS cols] of tile `t`, chunk `u` -> staging buffer (u & 1)
+    auto box_live = [&](int t, int u) {
+      const int tm0 = (t / tiles_n) * BM + quarter * 32, tn0 = (t % tiles_n) * BN + col_base + u * CPS;
+      return t < num_tiles && tm0 < p.M && tn0 < p.N;
+    };
+    auto prefetch_residual = [&](int t, int u) {
+      if (lane == 0 && box_live(t, u)) {
+        tma_store_wait_read<1>();                            // the store that last read this buffer (2 chunks ago) is done
+        mbar_expect_tx(&res_bar[ew], STAGING_BYTES);
+        tma_load_2d(my_staging + (u & 1) * STAGING_BYTES, &tm_res, &res_bar[ew],
+                    (t % tiles_n) * BN + col_base + u * CPS, (t / tiles_n) * BM + quarter * 32);
+      }
+    };
+    if (GATE) prefetch_residual(blockIdx.x, 0);
+
+    int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
@@ -201,7 +285,7 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
           const int n = n0 + i; const bool ok = n < p.N;
           float dw = ok ? p.delta_w[n] : 0.f;
           float bs = (ok && p.bias) ? load_bias(p.bias, p.bias_dtype, n) : 0.f;
-          if (EPI == B200Q_EPI_GATE_RESIDUAL && ok && p.gate) {   // (y*dw + b)*g == y*(dw*g) + b*g: fold the gate in
+          if (GATE && ok && p.gate) {                        // (y*dw + b)*g == y*(dw*g) + b*g: fold the gate in
             const float g = p.gate[n];
             dw *= g; bs *= g;
           }
@@ -211,77 +295,82 @@ gemm_w8a8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         named_bar_sync(1, EPI_WARPS * 32);
       }
-      const int row = m0 + ew * 32 + lane;
+      const int row = m0 + quarter * 32 + lane;
       const float da = (!RAW && row < p.M) ? p.delta_a[row] : 0.f;
       const int rs = (!RAW && p.rowsum_a && row < p.M) ? p.rowsum_a[row] : 0;   // only read when a zero point is in play
 
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
-      const uint32_t t_row = tmem_base + as * BN + ((uint32_t)(ew * 32) << 16);
+      const uint32_t t_row = tmem_base + as * BN + col_base + ((uint32_t)(quarter * 32) << 16);
 
-      for (int u = 0; u < BN / CPS; ++u) {
-        uint8_t* sbuf_ptr = my_staging + sbuf * STAGING_BYTES;
-        // the TMA store that last read this staging buffer must have finished reading it
-        if (lane == 0) tma_store_wait_read<1>();
-        __syncwarp();
-        const bool chunk_live = (n0 + u * CPS < p.N) && (m0 + ew * 32 < p.M);
-        if (EPI == B200Q_EPI_GATE_RESIDUAL && chunk_live) {
-          // pull the fp32 residual box [32 rows x CPS cols] into the staging buffer first
-          if (lane == 0) {
-            mbar_expect_tx(&res_bar[ew], STAGING_BYTES);
-            tma_load_2d(sbuf_ptr, &tm_res, &res_bar[ew], n0 + u * CPS, m0 + ew * 32);
-          }
+#pragma unroll 1
+      for (int u = 0; u < CHUNKS; ++u) {
+        uint8_t* sbuf_ptr = my_staging + (NBUF == 2 ? (u & 1) : 0) * STAGING_BYTES;
+        const bool live = box_live(tile, u);
+        if (GATE && live) {                                  // residual box prefetched one chunk ago has landed
+          mbar_wait(&res_bar[ew], res_phase);
+          res_phase ^= 1;
         }
+        uint4 o[CPS / ELEMS];                                // this thread's 128-byte output row, packed
 #pragma unroll
         for (int h = 0; h < CPS / 32; ++h) {
           uint32_t v[32];
           tmem_ld_32x32(t_row + u * CPS + h * 32, v);
           tmem_ld_wait();
-          if (u == BN / CPS - 1 && h == CPS / 32 - 1) {      // accumulator fully read: hand TMEM back to the MMA warp
+          if (u == CHUNKS - 1 && h == CPS / 32 - 1) {        // accumulator fully read: hand TMEM back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
           }
-          if (EPI == B200Q_EPI_GATE_RESIDUAL && chunk_live && h == 0) {
-            mbar_wait(&res_bar[ew], res_phase);
-            res_phase ^= 1;
-          }
 #pragma unroll
           for (int c = 0; c < 32 / ELEMS; ++c) {             // 16-byte chunks of this thread's row
-            const int col = u * CPS + h * 32 + c * ELEMS;    // column inside the tile
+            const int col = col_base + u * CPS + h * 32 + c * ELEMS;   // column inside the tile (multiple of 4)
             const int j = (h * 32) / ELEMS + c;              // chunk index inside the 128B staging row
-            uint4* dst = reinterpret_cast<uint4*>(sbuf_ptr + lane * 128 + ((j ^ (lane & 7)) << 4));
-            uint4 o;
             if (RAW) {
-              o = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
+              o[j] = make_uint4(v[c * 4], v[c * 4 + 1], v[c * 4 + 2], v[c * 4 + 3]);
             } else {
               float y[ELEMS];
 #pragma unroll
-              for (int e = 0; e < ELEMS; ++e) {
-                const int acc = (int)v[c * ELEMS + e] + (int)s_zp[col + e] * rs;
-                float t = fmaf((float)acc, da * s_dw[col + e], s_bias[col + e]);
-                if (EPI == B200Q_EPI_GELU_TANH) t = gelu_tanh(t);
-                y[e] = t;
+              for (int g4 = 0; g4 < ELEMS / 4; ++g4) {
+                const float4 dw4 = *reinterpret_cast<const float4*>(&s_dw[col + 4 * g4]);
+                const float4 b4 = *reinterpret_cast<const float4*>(&s_bias[col + 4 * g4]);
+                const short4 z4 = *reinterpret_cast<const short4*>(&s_zp[col + 4 * g4]);
+                const float dwv[4] = {dw4.x, dw4.y, dw4.z, dw4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
+                const int zv[4] = {z4.x, z4.y, z4.z, z4.w};
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const int acc = (int)v[c * ELEMS + 4 * g4 + e] + zv[e] * rs;
+                  float t = fmaf((float)acc, da * dwv[e], bv[e]);
+                  if (EPI == B200Q_EPI_GELU_TANH) t = gelu_tanh(t);
+                  y[4 * g4 + e] = t;
+                }
               }
-              if (EPI == B200Q_EPI_GATE_RESIDUAL) {
-                const uint4 r4 = *dst;                        // residual (fp32 x4) sits where the output goes
-                y[0] += __uint_as_float(r4.x);
-                y[1] += __uint_as_float(r4.y);
-                y[2] += __uint_as_float(r4.z);
-                y[3] += __uint_as_float(r4.w);
+              if (GATE) {                                    // residual (fp32 x4) sits where the output goes
+                const uint4 r4 = *reinterpret_cast<const uint4*>(sbuf_ptr + lane * 128 + ((j ^ (lane & 7)) << 4));
+                y[0] += __uint_as_float(r4.x); y[1] += __uint_as_float(r4.y);
+                y[2] += __uint_as_float(r4.z); y[3] += __uint_as_float(r4.w);
               }
-              o = pack_chunk<OutT>(y);
+              o[j] = pack_chunk<OutT>(y);
             }
-            *dst = o;
           }
         }
+        if (!GATE) {                                         // single staging buffer: the previous store must have read it
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int j = 0; j < CPS / ELEMS; ++j)
+          *reinterpret_cast<uint4*>(sbuf_ptr + lane * 128 + ((j ^ (lane & 7)) << 4)) = o[j];
         fence_proxy_async_smem();                            // generic-proxy smem writes -> visible to TMA
         __syncwarp();
         if (lane == 0) {
-          if (chunk_live) tma_store_2d(&tm_out, sbuf_ptr, n0 + u * CPS, m0 + ew * 32);
+          if (live) tma_store_2d(&tm_out, sbuf_ptr, n0 + col_base + u * CPS, m0 + quarter * 32);
           tma_store_commit();
         }
-        sbuf ^= 1;
+        if (GATE) {                                          // next box: next chunk of this tile, or chunk 0 of my next tile
+          if (u + 1 < CHUNKS) prefetch_residual(tile, u + 1);
+          else prefetch_residual(tile + (int)gridDim.x, 0);
+        }
       }
     }
     if (lane == 0) tma_store_wait<0>();
@@ -327,35 +416,36 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
   return B200Q_OK;
 }
 
-template <typename OutT, int EPI>
+template <typename OutT, int EPI, bool W4>
 static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                        const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_w8a8_kernel<OutT, EPI>;
+  auto kern = gemm_i8_kernel<OutT, EPI, W4>;
   static bool configured = false;    // cudaFuncSetAttribute once per instantiation, not per call
-  const int smem_bytes = GemmSmem::total;
+  const int smem_bytes = GemmSmem<W4, EPI>::total;
   if (!configured) {
     B200Q_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
   const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GEMM_THREADS, smem_bytes, st>>>(ta, tb, to, tr, p);
+  kern<<<grid, GemmSmem<W4, EPI>::threads, smem_bytes, st>>>(ta, tb, to, tr, p);
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
 
-template <typename OutT>
+template <typename OutT, bool W4>
 static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
                         const CUtensorMap& tr, const GemmParams& p, cudaStream_t st) {
   switch (epi) {
-    case B200Q_EPI_NONE: return launch_gemm<OutT, B200Q_EPI_NONE>(ta, tb, to, tr, p, st);
-    case B200Q_EPI_GELU_TANH: return launch_gemm<OutT, B200Q_EPI_GELU_TANH>(ta, tb, to, tr, p, st);
+    case B200Q_EPI_NONE: return launch_gemm<OutT, B200Q_EPI_NONE, W4>(ta, tb, to, tr, p, st);
+    case B200Q_EPI_GELU_TANH: return launch_gemm<OutT, B200Q_EPI_GELU_TANH, W4>(ta, tb, to, tr, p, st);
   }
   set_error("gemm: unsupported epilogue %d for this out_dtype", epi);
   return B200Q_ERR_BAD_ARG;
 }
 
-int gemm_i8_common(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw, const float* delta_a,
+template <bool W4>
+int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, const float* delta_a,
                    const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
                    void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
                    const float* residual, int64_t ldr, const float* gate, cudaStream_t st) {
@@ -364,9 +454,12 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw,
   B200Q_REQUIRE(K > 0, B200Q_ERR_BAD_ARG, "gemm: K must be > 0");
   B200Q_REQUIRE(M < (1ll << 31) && N < (1ll << 31) && K < (1ll << 31), B200Q_ERR_UNSUPPORTED, "gemm: dimension >= 2^31");
   B200Q_REQUIRE(qa && qw && out, B200Q_ERR_BAD_ARG, "gemm: null operand pointer");
-  B200Q_REQUIRE(lda >= K && ldw >= K && ldo >= N, B200Q_ERR_BAD_ARG, "gemm: leading dimension too small");
+  const int64_t kw_bytes = W4 ? ((K + 7) / 8) * 4 : K;      // bytes of one weight row
+  B200Q_REQUIRE(lda >= K && ldw >= kw_bytes && ldo >= N, B200Q_ERR_BAD_ARG, "gemm: leading dimension too small");
+  B200Q_REQUIRE(!W4 || rowsum_a != nullptr || out_dtype == B200Q_I32, B200Q_ERR_BAD_ARG,
+                "gemm_w4a8: rowsum_a is required (the unsigned-nibble bias is folded through the zero-point term)");
   B200Q_REQUIRE(lda % 16 == 0 && ldw % 16 == 0 && aligned(qa, 16) && aligned(qw, 16), B200Q_ERR_BAD_ARG,
-                "gemm: qa/qw must be 16-byte aligned with lda, ldw multiples of 16 (TMA global-stride rule)");
+                "gemm: qa/qw must be 16-byte aligned with lda, ldw (bytes) multiples of 16 (TMA global-stride rule)");
   const bool raw = out_dtype == B200Q_I32;
   if (!raw) {
     B200Q_REQUIRE(delta_a && delta_w, B200Q_ERR_BAD_ARG, "gemm: delta_a / delta_w required for dequantised output");
@@ -381,7 +474,11 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw,
   CUtensorMap ta, tb, to, tr;
   int rc;
   if ((rc = make_tmap_2d(&ta, qa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_tmap_2d(&tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if (W4) {
+    if ((rc = make_tmap_2d(&tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, kw_bytes, ldw, BN, BK / 2, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  } else {
+    if ((rc = make_tmap_2d(&tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  }
   CUtensorMapDataType odt = out_dtype == B200Q_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                             : out_dtype == B200Q_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
                             : out_dtype == B200Q_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
@@ -393,19 +490,20 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw,
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.delta_a = delta_a; p.delta_w = delta_w; p.zp_w = zp_w; p.rowsum_a = rowsum_a;
   p.bias = bias; p.bias_dtype = bias_dtype; p.gate = gate; p.epilogue = epilogue;
+  p.zp_offset = W4 ? -8 : 0;
 
-  if (raw) return launch_gemm<int32_t, B200Q_EPI_NONE>(ta, tb, to, tr, p, st);
+  if (raw) return launch_gemm<int32_t, B200Q_EPI_NONE, W4>(ta, tb, to, tr, p, st);
   if (epilogue == B200Q_EPI_GATE_RESIDUAL) {
     B200Q_REQUIRE(out_dtype == B200Q_F32, B200Q_ERR_BAD_ARG, "gemm: gate-residual epilogue writes the fp32 residual stream");
     B200Q_REQUIRE(residual != nullptr, B200Q_ERR_BAD_ARG, "gemm: residual required");
     B200Q_REQUIRE(ldr >= N && aligned(residual, 16) && (ldr * 4) % 16 == 0, B200Q_ERR_BAD_ARG, "gemm: bad residual layout");
     if ((rc = make_tmap_2d(&tr, residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    return launch_gemm<float, B200Q_EPI_GATE_RESIDUAL>(ta, tb, to, tr, p, st);
+    return launch_gemm<float, B200Q_EPI_GATE_RESIDUAL, W4>(ta, tb, to, tr, p, st);
   }
   switch (out_dtype) {
-    case B200Q_BF16: return dispatch_epi<__nv_bfloat16>(epilogue, ta, tb, to, tr, p, st);
-    case B200Q_F16: return dispatch_epi<__half>(epilogue, ta, tb, to, tr, p, st);
-    case B200Q_F32: return dispatch_epi<float>(epilogue, ta, tb, to, tr, p, st);
+    case B200Q_BF16: return dispatch_epi<__nv_bfloat16, W4>(epilogue, ta, tb, to, tr, p, st);
+    case B200Q_F16: return dispatch_epi<__half, W4>(epilogue, ta, tb, to, tr, p, st);
+    case B200Q_F32: return dispatch_epi<float, W4>(epilogue, ta, tb, to, tr, p, st);
   }
   return B200Q_ERR_BAD_ARG;
 }
@@ -420,15 +518,16 @@ extern "C" int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, 
                                int epilogue, const float* residual, int64_t ldr, const float* gate,
                                b200q_stream_t stream) {
   clear_error();
-  return gemm_i8_common(qa, lda, qw, ldw, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo, M, N,
-                        K, epilogue, residual, ldr, gate, (cudaStream_t)stream);
+  return gemm_i8_common<false>(qa, lda, qw, ldw, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo,
+                               M, N, K, epilogue, residual, ldr, gate, (cudaStream_t)stream);
 }
 
 namespace b200q {
-int gemm_w4a8_impl(const int8_t*, int64_t, const uint8_t*, int64_t, const float*, const float*, const float*,
-                   const int32_t*, const void*, int, void*, int, int64_t, int64_t, int64_t, int64_t, int, const float*,
-                   int64_t, const float*, cudaStream_t) {
-  set_error("gemm_w4a8: not built yet");
-  return B200Q_ERR_UNSUPPORTED;
+int gemm_w4a8_impl(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4, const float* delta_a,
+                   const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                   void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
+                   const float* residual, int64_t ldr, const float* gate, cudaStream_t st) {
+  return gemm_i8_common<true>(qa, lda, qw4, ldw4, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo,
+                              M, N, K, epilogue, residual, ldr, gate, st);
 }
 }  // namespace b200q

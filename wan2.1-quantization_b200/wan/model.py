@@ -9,7 +9,7 @@ all ten linears of a block are integer GEMMs and every token-local stage is one 
     x (fp32 residual stream, [L, D])
       ln_mod_quant(norm1, e0/e1)            -> int8 codes, per-token delta, rowsum        (1 kernel)
       gemm_w8a8  [L,D]x[3D,D]  (q|k|v fused: same activation codes)        -> bf16 [L,3D]  (1 kernel)
-      RMSNorm(q), RMSNorm(k) over D, 3-axis RoPE (model.py:43-89)                          (torch ops; next-row f-4)
+      rmsnorm_rope(q), rmsnorm_rope(k): RMSNorm over D + 3-axis RoPE (model.py:43-89)       (1 kernel each)
       attention                                                   (library flash attention, or the int8 path)
       quant_rows(attn_out) -> gemm_w8a8 'o' with epilogue x += y*e2                        (2 kernels)
       ln_mod_quant(norm3 affine) -> q gemm ; context: quant_rows -> [T,D]x[2D,D] k|v gemm ; attention ; o gemm (+x)
@@ -122,11 +122,21 @@ def qlinear(qa, da, rowsum, w: QWeight, out_dtype=torch.bfloat16, epilogue=b200q
 
 
 # ------------------------------------------------------------------------------------------------------------
-# RoPE tables / RMSNorm (host-of-the-path pieces; fp32/bf16 torch ops)
+# RoPE tables (host, float64, cached) / fused RMSNorm+RoPE kernel / library attention core
 # ------------------------------------------------------------------------------------------------------------
+_ROPE_CACHE = {}
+
+
 def rope_table(head_dim, grid, device, pos_offset=0, length=None):
-    """cos/sin [L, head_dim/2] fp32 for the 3-axis RoPE of model.py:31-70, 527-533 (computed in float64).
-    pos_offset/length select a rank's token chunk (xdit_context_parallel.py:52-58)."""
+    """cos/sin [L, head_dim/2] fp32 for the 3-axis RoPE of model.py:31-70, 527-533 (computed in float64, cached per
+    shape).  pos_offset/length select a rank's token chunk (xdit_context_parallel.py:52-58)."""
+    key = (head_dim, tuple(grid), str(device), pos_offset, length)
+    if key not in _ROPE_CACHE:
+        _ROPE_CACHE[key] = _rope_table(head_dim, grid, device, pos_offset, length)
+    return _ROPE_CACHE[key]
+
+
+def _rope_table(head_dim, grid, device, pos_offset=0, length=None):
     d = head_dim
     dims = [d - 4 * (d // 6), 2 * (d // 6), 2 * (d // 6)]
 
@@ -144,18 +154,9 @@ def rope_table(head_dim, grid, device, pos_offset=0, length=None):
 
 
 def rmsnorm_rope(x, weight, eps, cos=None, sin=None, num_heads=1):
-    """WanRMSNorm over the FULL model dim (model.py:73-89, 127-128) then optional RoPE on [L, H, hd] pairs.
-    x bf16 [L, D] (may be a strided column slice) -> bf16 [L, D] contiguous."""
-    xf = x.float()
-    y = xf * torch.rsqrt(xf.pow(2).mean(dim=-1, keepdim=True) + eps)
-    y = y.to(x.dtype).float() * weight                       # .type_as(x) * weight
-    if cos is not None:
-        L, D = y.shape
-        yp = y.view(L, num_heads, D // num_heads // 2, 2)
-        a, b = yp[..., 0], yp[..., 1]
-        c, s = cos[:, None, :], sin[:, None, :]
-        y = torch.stack((a * c - b * s, a * s + b * c), dim=-1).view(L, D)
-    return y.to(torch.bfloat16)
+    """WanRMSNorm over the FULL model dim (model.py:73-89, 127-128) then optional RoPE on [L, H, hd] pairs: one fused
+    kernel.  x bf16 [L, D] (may be a strided column slice of the fused qkv output) -> bf16 [L, D] contiguous."""
+    return b200q.rmsnorm_rope(x, weight, eps, cos, sin, x.shape[1] // num_heads)
 
 
 def sdpa(q, k, v, num_heads):
