@@ -131,6 +131,10 @@ B200Q_API int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, i
                     int epilogue, const float* residual, int64_t ldr, const float* gate,
                     b200q_stream_t stream);
 
+/* Tile-scheduling knob for both GEMMs (debug / benchmarking): 0 = automatic (default), 1 = single-CTA tiles only,
+ * 2 = 2-CTA clusters with TMA-multicast B tiles whenever the problem has >= 2 row blocks.  Results are identical. */
+B200Q_API int b200q_gemm_set_cluster(int mode);
+
 /* codes int8 [N,K] in [-8,7] -> packed uint8 [N, ceil(K/8)*4].  Format (consumed by b200q_gemm_w4a8's in-smem
  * unpacker): K is split in groups of 8 codes; byte i (i=0..3) of the group's 32-bit word holds (code[i]+8) in bits 0-3
  * and (code[4+i]+8) in bits 4-7.  Nibbles are unsigned (the +8 bias is folded into the GEMM's zero-point term, the

@@ -95,3 +95,29 @@ def test_rmsnorm_rope_kernel(dev, L, heads, hd, grid):
     assert c >= 0.99999
     out2 = b200q.rmsnorm_rope(x.to(dev)[:, :D], w.to(dev), 1e-6).cpu().float()
     assert float((out2 - O.rms_norm(x[:, :D], w, 1e-6)).abs().max()) <= 2e-2 * float(out2.abs().max())
+
+
+def test_quantized_attention_parity_mode(dev, golden_dir):
+    """Materialised quantized attention (quant_opensora.py:430-478, 'row' attn-map group) vs the golden vectors of the
+    imported reference quantizers: Q/K/V deltas and dequantised tensors bit-exact; P codes within one step (S comes
+    from the int8 GEMM's fp32 epilogue instead of an fp32 matmul); output cosine >= 0.9999."""
+    import os
+    from wan.attention_q import quantized_attention_parity
+    rec = torch.load(os.path.join(golden_dir, "quant_attention.pt"))
+    B, H, L, hd = rec["q"].shape
+    to_tok = lambda t: t[0].permute(1, 0, 2).reshape(L, H * hd).contiguous().to(dev)      # [1,H,L,hd] -> [L, H*hd]
+    out, info = quantized_attention_parity(to_tok(rec["q"]), to_tok(rec["k"]), to_tok(rec["v"]), H, return_info=True)
+    # reference deltas are [B*H*L, 1] in (h, l) order; ours are [L, H]
+    assert torch.equal(info["dq"].t().reshape(-1).cpu(), rec["q_delta"].flatten())
+    assert torch.equal(info["dk"].t().reshape(-1).cpu(), rec["k_delta"].flatten())
+    assert torch.equal(info["dv"].cpu(), rec["v_delta"].flatten())
+    q_dq = (info["qq"].float() * info["dq"].repeat_interleave(hd, dim=1)).cpu()
+    assert torch.equal(q_dq, to_tok(rec["q_dequant"]).cpu())
+    for h in range(H):
+        pdq = ((info["pq"][h].float() + info["zp"][h][:, None]) * info["dp"][h][:, None]).t().cpu()   # [Lq, Lk]
+        ref = rec["attn_quant"][0, h]
+        step = rec["p_delta"].reshape(H, L)[h]
+        assert float(((pdq - ref).abs() / step[None, :]).max()) <= 1.0 + 1e-3
+    ref_out = rec["out"][0].permute(1, 0, 2).reshape(L, H * hd)
+    c = float((out.cpu().double().flatten() @ ref_out.double().flatten()) / (out.cpu().double().norm() * ref_out.double().norm()))
+    assert c >= 0.9999, c

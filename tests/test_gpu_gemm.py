@@ -204,3 +204,33 @@ def test_w4a8_gelu_and_gate_epilogues(dev):
     b200q.gemm_w4a8(qa.to(dev), packed, K, da.to(dev), dw.to(dev), zp.to(dev), rs.to(dev), None,
                     epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=gate.to(dev))
     assert float((x.cpu().double() - (res.double() + y * gate.double())).abs().max()) <= 1e-4
+
+
+# ---- 2-CTA cluster / TMA-multicast scheduling: identical results ----------------------------------------------
+@pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 512, 1536), (130, 272, 144), (1000, 1536, 512), (129, 8, 16)])
+def test_cluster_multicast_bit_exact(dev, M, N, K):
+    qa, qw = _codes(M, K, M + K + 5), _codes(N, K, N + K + 6, -128, 127)
+    ref = O.int_accumulators(qa, qw)
+    try:
+        b200q.gemm_set_cluster(2)
+        acc = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), out_dtype=torch.int32)
+        assert torch.equal(acc.cpu(), ref)
+        # W4 converters + remote barrier arrives
+        qw4 = _codes(N, K, 7, -8, 7)
+        da = torch.rand(M) * 0.01 + 0.005
+        dw = torch.rand(N) * 0.1 + 0.1
+        rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+        out = b200q.gemm_w4a8(qa.to(dev), b200q.pack_w4(qw4.to(dev)), K, da.to(dev), dw.to(dev), None, rs.to(dev), None,
+                              out_dtype=torch.float32)
+        ref4 = da.double()[:, None] * dw.double()[None, :] * O.int_accumulators(qa, qw4).double()
+        assert float(((out.cpu().double() - ref4).abs() / (ref4.abs() + 1.0)).max()) <= 2e-5
+        # gate-residual epilogue (3-stage ring, prefetched residual boxes) under clusters
+        res = torch.randn(M, N)
+        gate = torch.randn(N)
+        x = res.clone().to(dev)
+        b200q.gemm_w8a8(qa.to(dev), qw.to(dev), da.to(dev), dw.to(dev), None, None, None, epilogue=b200q.EPI_GATE_RESIDUAL,
+                        residual=x, gate=gate.to(dev))
+        y = da.double()[:, None] * dw.double()[None, :] * ref.double()
+        assert float((x.cpu().double() - (res.double() + y * gate.double())).abs().max()) <= 1e-3 * float(y.abs().max() + 1)
+    finally:
+        b200q.gemm_set_cluster(0)

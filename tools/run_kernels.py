@@ -1,0 +1,44 @@
+"""Short driver for ncu captures: launches each hot kernel a few times at the BASELINE shapes (1.3B, L=32760)."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "wan2.1-quantization_b200"))
+import b200q  # noqa: E402
+
+dev = torch.device("cuda:0")
+L, D, Fd = 32760, 1536, 8960
+torch.manual_seed(0)
+x32 = torch.randn(L, D, device=dev)
+h16 = torch.randn(L, Fd, device=dev, dtype=torch.bfloat16)
+sh = torch.randn(D, device=dev) * 0.1
+stat = torch.zeros(D, device=dev)
+qa = torch.randint(-127, 128, (L, D), dtype=torch.int8, device=dev)
+qh = torch.randint(-127, 128, (L, Fd), dtype=torch.int8, device=dev)
+w_dd = torch.randint(-128, 128, (D, D), dtype=torch.int8, device=dev)
+w_fd = torch.randint(-128, 128, (Fd, D), dtype=torch.int8, device=dev)
+w_df = torch.randint(-128, 128, (D, Fd), dtype=torch.int8, device=dev)
+w4 = b200q.pack_w4(torch.randint(-8, 8, (Fd, D), dtype=torch.int8, device=dev))
+da = torch.rand(L, device=dev) * 1e-2
+rs = torch.randint(-1000, 1000, (L,), dtype=torch.int32, device=dev)
+dwd, dwf = torch.rand(D, device=dev) * 1e-2, torch.rand(Fd, device=dev) * 1e-2
+zd, zf = torch.ones(D, device=dev), torch.ones(Fd, device=dev)
+bd, bf = torch.rand(D, device=dev), torch.rand(Fd, device=dev)
+res = torch.randn(L, D, device=dev)
+qkv = torch.randn(L, 3 * D, device=dev, dtype=torch.bfloat16)
+cos = torch.rand(L, 64, device=dev); sin = torch.rand(L, 64, device=dev)
+for _ in range(3):
+    b200q.quant_rows(x32, 8, True, True)
+    b200q.quant_rows(h16, 8, True, True)
+    b200q.calib_update(x32, stat)
+    b200q.ln_mod_quant(x32, 1e-6, None, None, sh, sh, 8)
+    b200q.rmsnorm_rope(qkv[:, :D], dwd, 1e-6, cos, sin, 128)
+    b200q.gemm_w8a8(qa, w_dd, da, dwd, zd, rs, bd)                                             # D->D, bf16 out
+    b200q.gemm_w8a8(qa, w_fd, da, dwf, zf, rs, bf, epilogue=b200q.EPI_GELU_TANH)               # D->F + GELU
+    b200q.gemm_w8a8(qh, w_df, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # F->D
+    b200q.gemm_w8a8(qa, w_dd, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # D->D gate
+    b200q.gemm_w4a8(qa, w4, D, da, dwf, zf, rs, bf)
+torch.cuda.synchronize()
+print("ok", b200q.launch_count)

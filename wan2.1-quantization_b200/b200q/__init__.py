@@ -50,6 +50,7 @@ _SIGNATURES = {
     "b200q_gemm_w4a8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
                                 c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+    "b200q_gemm_set_cluster": (c_int, [c_int]),
     "b200q_pack_w4": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_ln_mod_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
                                    c_void_p, c_void_p, c_int, c_void_p, c_int64, c_void_p, c_void_p,
@@ -312,3 +313,10 @@ def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0):
                                    _ptr(sin), int(head_dim), _ptr(out), _ld(out), _stream())
     _check(rc, "b200q_rmsnorm_rope")
     return out
+
+
+def gemm_set_cluster(mode):
+    """0 auto, 1 single-CTA tiles, 2 force 2-CTA multicast clusters (results identical; scheduling knob)."""
+    rc = load().b200q_gemm_set_cluster(int(mode))
+    if rc != 0:
+        raise B200QError("b200q_gemm_set_cluster: bad mode")

@@ -39,6 +39,30 @@ int sm_count();   // cached multiProcessorCount of the current device (148 on B2
 
 static inline bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
+// Row-in-registers kernels (quantizer, LN+quant, RMSNorm+RoPE): a row of `kv` 16-byte vectors is owned by W warps, each
+// thread holding V vectors.  Per-warp fixed work (reductions, row parameters) is amortised over V*32 vectors, so pick
+// the FEWEST warps whose V fits the register budget; W == 1 needs no block barrier at all.
+struct RowLayout { int W, V, threads; };
+static inline RowLayout pick_row_layout(int kv, int vmax) {
+  RowLayout r{1, 0, 256};
+  while (r.W < 8 && (kv + 32 * r.W - 1) / (32 * r.W) > vmax) r.W *= 2;
+  if ((kv + 32 * r.W - 1) / (32 * r.W) > vmax) { r.W = 32; r.threads = 1024; }
+  r.V = (kv + 32 * r.W - 1) / (32 * r.W);
+  return r;
+}
+// dispatch a runtime V onto the instantiated set {1,2,3,4,6,8,10,12}
+#define B200Q_DISPATCH_V(V, CALL)                 \
+  do {                                            \
+    if ((V) <= 1) { CALL(1); }                    \
+    else if ((V) <= 2) { CALL(2); }               \
+    else if ((V) <= 3) { CALL(3); }               \
+    else if ((V) <= 4) { CALL(4); }               \
+    else if ((V) <= 6) { CALL(6); }               \
+    else if ((V) <= 8) { CALL(8); }               \
+    else if ((V) <= 10) { CALL(10); }             \
+    else { CALL(12); }                            \
+  } while (0)
+
 // ---- dtype helpers ------------------------------------------------------------------------
 template <typename T> struct DType;
 template <> struct DType<float>         { static constexpr int id = B200Q_F32;  static constexpr int vec = 4; };

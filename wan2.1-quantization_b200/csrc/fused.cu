@@ -34,24 +34,23 @@ __device__ __forceinline__ uint32_t pack4i(int c0, int c1, int c2, int c3) {
   return __byte_perm(t0, t1, 0x5410);
 }
 
-// cross-warp (within one row's warps) reductions through shared memory
-__device__ __forceinline__ float row_reduce_sum(float v, float* s_buf, int warp, int lane, int w0, int wpr) {
+// cross-warp (within one row's warps) reductions: one smem hop + one barrier; every call site owns its smem slot
+__device__ __forceinline__ float row_reduce_sum(float v, float* s_slot, int warp, int lane, int w0, int wpr) {
   v = warp_sum(v);
   if (wpr > 1) {
-    __syncthreads();                      // protect s_buf reuse
-    if (lane == 0) s_buf[warp] = v;
+    if (lane == 0) s_slot[warp] = v;
     __syncthreads();
-    v = warp_sum(lane < wpr ? s_buf[w0 + lane] : 0.f);
+    v = 0.f;
+    for (int i = 0; i < wpr; ++i) v += s_slot[w0 + i];
   }
   return v;
 }
-__device__ __forceinline__ float row_reduce_max(float v, float* s_buf, int warp, int lane, int w0, int wpr) {
+__device__ __forceinline__ float row_reduce_max(float v, float* s_slot, int warp, int lane, int w0, int wpr) {
   v = warp_max(v);
   if (wpr > 1) {
+    if (lane == 0) s_slot[warp] = v;
     __syncthreads();
-    if (lane == 0) s_buf[warp] = v;
-    __syncthreads();
-    v = warp_max(lane < wpr ? s_buf[w0 + lane] : 0.f);
+    for (int i = 0; i < wpr; ++i) v = fmaxf(v, s_slot[w0 + i]);
   }
   return v;
 }
@@ -60,11 +59,11 @@ template <typename T, typename YT, int V, int THREADS>
 __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, const int warps_per_row) {
   using VT = Vec16<T>;
   constexpr int N = VT::N;
-  __shared__ float s_buf[32];
+  __shared__ float s_buf[3][32];
   __shared__ int s_sum[32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_per_cta = (blockDim.x >> 5) / warps_per_row;
+  const int rows_per_cta = (THREADS / 32) / warps_per_row;
   const int row_in_cta = warp / warps_per_row;
   const int w0 = row_in_cta * warps_per_row;
   const int wr = warp - w0;
@@ -86,7 +85,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
 #pragma unroll
     for (int i = 0; i < N; ++i) s += f[v][i];
   }
-  const float mean = row_reduce_sum(s, s_buf, warp, lane, w0, warps_per_row) * inv_c;
+  const float mean = row_reduce_sum(s, s_buf[0], warp, lane, w0, warps_per_row) * inv_c;
   float ss = 0.f;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
@@ -97,7 +96,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
       ss += live ? d * d : 0.f;
     }
   }
-  const float var = row_reduce_sum(ss, s_buf, warp, lane, w0, warps_per_row) * inv_c;
+  const float var = row_reduce_sum(ss, s_buf[1], warp, lane, w0, warps_per_row) * inv_c;
   const float rstd = __frsqrt_rn(var + a.eps);
 
   float amax = 0.f;
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   }
   if (a.q == nullptr) return;       // uniform across the CTA
 
-  amax = row_reduce_max(amax, s_buf, warp, lane, w0, warps_per_row);
+  amax = row_reduce_max(amax, s_buf[2], warp, lane, w0, warps_per_row);
   float delta = __fdiv_rn(amax, a.n_levels);
   if (delta < 1.0e-6f) delta = 1.0e-6f;                                   // base_quantizer.py:122-128
   const float r = __frcp_rn(delta);
@@ -170,10 +169,12 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   if (a.rowsum != nullptr) {
     sum = warp_sum(sum);
     if (warps_per_row > 1) {
-      __syncthreads();
       if (lane == 0) s_sum[warp] = sum;
       __syncthreads();
-      sum = warp_sum(lane < warps_per_row ? s_sum[w0 + lane] : 0);
+      if (t == 0) {
+        sum = 0;
+        for (int i = 0; i < warps_per_row; ++i) sum += s_sum[w0 + i];
+      }
     }
     if (row_ok && t == 0) a.rowsum[row] = sum;
   }
@@ -184,23 +185,20 @@ template <typename T, typename YT>
 static int launch_ln(const LnArgs& a, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   const int kv = (int)(a.cols / N);
-  int W = 1;
-  while (W < 8 && (kv + 32 * W - 1) / (32 * W) > 4) W *= 2;
-  int threads = 256;
-  if ((kv + 32 * W - 1) / (32 * W) > 8) { W = 32; threads = 1024; }
-  const int V = (kv + 32 * W - 1) / (32 * W);
-  B200Q_REQUIRE(V <= 8, B200Q_ERR_UNSUPPORTED, "ln_mod_quant: cols=%lld too large (max %d)", (long long)a.cols, 8 * 1024 * N);
-  const int rows_per_cta = (threads / 32) / W;
+  const RowLayout lay = pick_row_layout(kv, N == 4 ? 12 : 6);        // fp32 values live in registers: 48 per thread
+  const int W = lay.W, V = lay.V;
+  B200Q_REQUIRE(V <= 12 && (lay.threads == 256 || V <= 8), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: cols=%lld too large",
+                (long long)a.cols);
+  const int rows_per_cta = (lay.threads / 32) / W;
   const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
-#define B200Q_LN(VV, TH) ln_mod_quant_kernel<T, YT, VV, TH><<<grid, TH, 0, st>>>(a, W)
-  if (threads == 1024) { if (V <= 4) B200Q_LN(4, 1024); else B200Q_LN(8, 1024); }
-  else if (V <= 1) B200Q_LN(1, 256);
-  else if (V <= 2) B200Q_LN(2, 256);
-  else if (V <= 3) B200Q_LN(3, 256);
-  else if (V <= 4) B200Q_LN(4, 256);
-  else if (V <= 6) B200Q_LN(6, 256);
-  else B200Q_LN(8, 256);
+  if (lay.threads == 1024) {
+    if (V <= 4) ln_mod_quant_kernel<T, YT, 4, 1024><<<grid, 1024, 0, st>>>(a, W);
+    else ln_mod_quant_kernel<T, YT, 8, 1024><<<grid, 1024, 0, st>>>(a, W);
+  } else {
+#define B200Q_LN(VV) ln_mod_quant_kernel<T, YT, VV, 256><<<grid, 256, 0, st>>>(a, W)
+    B200Q_DISPATCH_V(V, B200Q_LN);
 #undef B200Q_LN
+  }
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
@@ -228,7 +226,7 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
   constexpr int N = VT::N;            // 8 (bf16 / fp16)
   __shared__ float s_buf[32];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_per_cta = (blockDim.x >> 5) / warps_per_row;
+  const int rows_per_cta = (THREADS / 32) / warps_per_row;
   const int row_in_cta = warp / warps_per_row;
   const int w0 = row_in_cta * warps_per_row;
   const int wr = warp - w0;
@@ -287,23 +285,19 @@ template <typename T>
 static int launch_rope(const RopeArgs& a, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   const int kv = (int)(a.cols / N);
-  int W = 1;
-  while (W < 8 && (kv + 32 * W - 1) / (32 * W) > 3) W *= 2;
-  int threads = 256;
-  if ((kv + 32 * W - 1) / (32 * W) > 8) { W = 32; threads = 1024; }
-  const int V = (kv + 32 * W - 1) / (32 * W);
+  const RowLayout lay = pick_row_layout(kv, 6);                     // 8 fp32 values per vector: 48 registers per thread
+  const int W = lay.W, V = lay.V;
   B200Q_REQUIRE(V <= 8, B200Q_ERR_UNSUPPORTED, "rmsnorm_rope: cols=%lld too large", (long long)a.cols);
-  const int rows_per_cta = (threads / 32) / W;
+  const int rows_per_cta = (lay.threads / 32) / W;
   const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
-#define B200Q_RR(VV, TH) rmsnorm_rope_kernel<T, VV, TH><<<grid, TH, 0, st>>>(a, W)
-  if (threads == 1024) { if (V <= 4) B200Q_RR(4, 1024); else B200Q_RR(8, 1024); }
-  else if (V <= 1) B200Q_RR(1, 256);
-  else if (V <= 2) B200Q_RR(2, 256);
-  else if (V <= 3) B200Q_RR(3, 256);
-  else if (V <= 4) B200Q_RR(4, 256);
-  else if (V <= 6) B200Q_RR(6, 256);
-  else B200Q_RR(8, 256);
+  if (lay.threads == 1024) {
+    if (V <= 4) rmsnorm_rope_kernel<T, 4, 1024><<<grid, 1024, 0, st>>>(a, W);
+    else rmsnorm_rope_kernel<T, 8, 1024><<<grid, 1024, 0, st>>>(a, W);
+  } else {
+#define B200Q_RR(VV) rmsnorm_rope_kernel<T, VV, 256><<<grid, 256, 0, st>>>(a, W)
+    B200Q_DISPATCH_V(V, B200Q_RR);
 #undef B200Q_RR
+  }
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }

@@ -40,10 +40,10 @@ constexpr int TMEM_COLS = 512;
 //       of two 32 KB SWIZZLE_128B int8 tiles that the MMA reads.
 // The gate-residual epilogue (8 B/element of HBM traffic: memory-bound) trades one ring stage for a second staging
 // buffer per epilogue warp so the residual box of chunk u+1 is in flight while chunk u is processed.
-template <bool W4, int EPI>
+template <bool W4, int NSTAGE>
 struct GemmSmem {
-  static constexpr int stages = (EPI == B200Q_EPI_GATE_RESIDUAL) ? 3 : 4;
-  static constexpr int staging_bufs = (EPI == B200Q_EPI_GATE_RESIDUAL) ? 2 : 1;
+  static constexpr int stages = NSTAGE;                      // 4, or 3 with double-buffered staging (short-K gate-residual)
+  static constexpr int staging_bufs = (NSTAGE == 3) ? 2 : 1;
   static constexpr int b_stage = W4 ? B_BYTES / 2 : B_BYTES;
   static constexpr int stage = A_BYTES + b_stage;
   static constexpr int ring = 0;
@@ -109,8 +109,11 @@ __device__ __forceinline__ uint4 pack_chunk(const float* y) {
 }
 
 // OutT = int32_t -> raw accumulators.  EPI: b200q_epilogue.
-template <typename OutT, int EPI, bool W4>
-__global__ void __launch_bounds__(GemmSmem<W4, EPI>::threads, 1)
+// CL = CTAs per cluster (1 or 2).  CL == 2: the two CTAs of a cluster work on vertically adjacent tiles (same n0);
+// each loads its own A tile and HALF of the shared B tile, multicast into both CTAs' smem, which cuts the L2->SM
+// operand traffic per tile from 48 KB to 32 KB per K-block (the int8 MMA rate is L2-bandwidth-bound at 128x256 tiles).
+template <typename OutT, int EPI, bool W4, int NSTAGE, int CL>
+__global__ void __launch_bounds__(GemmSmem<W4, NSTAGE>::threads, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                  const GemmParams p) {
@@ -119,7 +122,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  using SM = GemmSmem<W4, EPI>;
+  using SM = GemmSmem<W4, NSTAGE>;
   constexpr int STAGE_BYTES = SM::stage;
   constexpr int STAGES = SM::stages;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::barriers);
@@ -133,13 +136,21 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_n = (p.N + BN - 1) / BN, tiles_m = (p.M + BM - 1) / BM;
-  const int num_tiles = tiles_m * tiles_n;
+  // a "tile" index below is a CLUSTER tile: CL vertically adjacent 128-row blocks sharing one 256-column block
+  const int num_tiles = ((tiles_m + CL - 1) / CL) * tiles_n;
   const int num_kb = (p.K + BK - 1) / BK;
+  const int cta_rank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int first_tile = (int)blockIdx.x / CL, tile_step = (int)gridDim.x / CL;
+  auto tile_m0 = [&](int t) { return ((t / tiles_n) * CL + cta_rank) * BM; };
+  auto tile_n0 = [&](int t) { return (t % tiles_n) * BN; };
+  constexpr uint16_t kAllCtas = (uint16_t)((1u << CL) - 1);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], W4 ? 1 + CVT_WARPS : 1);        // W4: the packed tile is also released by the converters
+      // a ring slot is free when every MMA warp (and, for W4, every converter warp) of the CLUSTER is done with it:
+      // with CL == 2 the peer multicasts half of B into this CTA's slot
+      mbar_init(&empty_bar[s], CL * (W4 ? 1 + CVT_WARPS : 1));
     }
     for (int s = 0; s < UNPACK_BUFS; ++s) { mbar_init(&bready_bar[s], CVT_WARPS); mbar_init(&bfree_bar[s], 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
@@ -153,6 +164,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync();                                 // peer's barriers are initialised before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_base_slot;
 
@@ -160,14 +172,19 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
+        const int m0 = tile_m0(tile), n0 = tile_n0(tile);
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + SM::ring + stage * STAGE_BYTES;
-          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);
+          mbar_expect_tx(&full_bar[stage], STAGE_BYTES);       // own A + both halves of B (one arrives from the peer)
           tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
-          tma_load_2d(sa + A_BYTES, &tm_b, &full_bar[stage], W4 ? kb * (BK / 2) : kb * BK, n0);
+          if (CL == 2) {
+            tma_load_2d_mc(sa + A_BYTES + cta_rank * (SM::b_stage / 2), &tm_b, &full_bar[stage],
+                           W4 ? kb * (BK / 2) : kb * BK, n0 + cta_rank * (BN / 2), kAllCtas);
+          } else {
+            tma_load_2d(sa + A_BYTES, &tm_b, &full_bar[stage], W4 ? kb * (BK / 2) : kb * BK, n0);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -178,7 +195,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       constexpr uint32_t idesc = make_i8_idesc(BM, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       int ub = 0; uint32_t uphase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
         const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
         mbar_wait(&tmem_empty_bar[as], aphase ^ 1);          // epilogue has drained this accumulator
         tcgen05_fence_after();
@@ -196,7 +213,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
             mma_i8_ss(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc,
                       (kb | k) != 0 ? 1u : 0u);
           }
-          mma_commit(&empty_bar[stage]);                     // slot free once these MMAs have read it
+          if (CL == 2) mma_commit_mc(&empty_bar[stage], kAllCtas);   // releases the slot in BOTH CTAs
+          else mma_commit(&empty_bar[stage]);                // slot free once these MMAs have read it
           if (W4) {
             mma_commit(&bfree_bar[ub]);
             if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
@@ -213,7 +231,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     // (the +8 bias is folded into the zero-point term of the epilogue).
     const int ct = threadIdx.x - (CTRL_WARPS + EPI_WARPS) * 32;
     int stage = 0; uint32_t phase = 0; int ub = 0; uint32_t uphase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step) {
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         mbar_wait(&bfree_bar[ub], uphase ^ 1);
@@ -236,6 +254,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         if (lane == 0) {
           mbar_arrive(&bready_bar[ub]);
           mbar_arrive(&empty_bar[stage]);                  // this warp is done reading the packed tile
+          if (CL == 2) mbar_arrive_remote(&empty_bar[stage], cta_rank ^ 1);   // ... which the peer half-fills
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
@@ -262,22 +281,22 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
     // residual prefetch (GATE): box [32 rows x CPS cols] of tile `t`, chunk `u` -> staging buffer (u & 1)
     auto box_live = [&](int t, int u) {
-      const int tm0 = (t / tiles_n) * BM + quarter * 32, tn0 = (t % tiles_n) * BN + col_base + u * CPS;
-      return t < num_tiles && tm0 < p.M && tn0 < p.N;
+      return t < num_tiles && tile_m0(t) + quarter * 32 < p.M && tile_n0(t) + col_base + u * CPS < p.N;
     };
     auto prefetch_residual = [&](int t, int u) {
       if (lane == 0 && box_live(t, u)) {
-        tma_store_wait_read<1>();                            // the store that last read this buffer (2 chunks ago) is done
+        if (NBUF == 2) tma_store_wait_read<1>();             // the store that last read this buffer (2 chunks ago) is done
+        else tma_store_wait_read<0>();
         mbar_expect_tx(&res_bar[ew], STAGING_BYTES);
-        tma_load_2d(my_staging + (u & 1) * STAGING_BYTES, &tm_res, &res_bar[ew],
-                    (t % tiles_n) * BN + col_base + u * CPS, (t / tiles_n) * BM + quarter * 32);
+        tma_load_2d(my_staging + (NBUF == 2 ? (u & 1) : 0) * STAGING_BYTES, &tm_res, &res_bar[ew],
+                    tile_n0(t) + col_base + u * CPS, tile_m0(t) + quarter * 32);
       }
     };
-    if (GATE) prefetch_residual(blockIdx.x, 0);
+    if (GATE && NBUF == 2) prefetch_residual(first_tile, 0);
 
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+    for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
+      const int m0 = tile_m0(tile), n0 = tile_n0(tile);
       const int as = it & 1; const uint32_t aphase = (it >> 1) & 1;
       if (!RAW) {
         named_bar_sync(1, EPI_WARPS * 32);                   // everyone finished reading the previous tile's params
@@ -307,6 +326,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int u = 0; u < CHUNKS; ++u) {
         uint8_t* sbuf_ptr = my_staging + (NBUF == 2 ? (u & 1) : 0) * STAGING_BYTES;
         const bool live = box_live(tile, u);
+        if (GATE && NBUF == 1) prefetch_residual(tile, u);   // long-K variant: no spare buffer, load in place
         if (GATE && live) {                                  // residual box prefetched one chunk ago has landed
           mbar_wait(&res_bar[ew], res_phase);
           res_phase ^= 1;
@@ -367,9 +387,9 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (live) tma_store_2d(&tm_out, sbuf_ptr, n0 + col_base + u * CPS, m0 + quarter * 32);
           tma_store_commit();
         }
-        if (GATE) {                                          // next box: next chunk of this tile, or chunk 0 of my next tile
+        if (GATE && NBUF == 2) {                             // next box: next chunk of this tile, or chunk 0 of my next tile
           if (u + 1 < CHUNKS) prefetch_residual(tile, u + 1);
-          else prefetch_residual(tile + (int)gridDim.x, 0);
+          else prefetch_residual(tile + tile_step, 0);
         }
       }
     }
@@ -378,6 +398,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync();                                 // the peer may still signal this CTA's barriers / fill its smem
   tcgen05_fence_after();
   if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
 }
@@ -416,29 +437,57 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
   return B200Q_OK;
 }
 
-template <typename OutT, int EPI, bool W4>
-static int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
-                       const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_i8_kernel<OutT, EPI, W4>;
+template <typename OutT, int EPI, bool W4, int NSTAGE, int CL>
+static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
+                          const GemmParams& p, cudaStream_t st) {
+  auto kern = gemm_i8_kernel<OutT, EPI, W4, NSTAGE, CL>;
   static bool configured = false;    // cudaFuncSetAttribute once per instantiation, not per call
-  const int smem_bytes = GemmSmem<W4, EPI>::total;
+  const int smem_bytes = GemmSmem<W4, NSTAGE>::total;
   if (!configured) {
     B200Q_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
   }
-  const int tiles = ((p.M + BM - 1) / BM) * ((p.N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  kern<<<grid, GemmSmem<W4, EPI>::threads, smem_bytes, st>>>(ta, tb, to, tr, p);
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  const int cluster_tiles = ((tiles_m + CL - 1) / CL) * tiles_n;
+  int grid = cluster_tiles * CL;
+  const int cap = (sm_count() / CL) * CL;                      // persistent: one CTA per SM, whole clusters only
+  if (grid > cap) grid = cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3((unsigned)GemmSmem<W4, NSTAGE>::threads);
+  cfg.dynamicSmemBytes = (size_t)smem_bytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  B200Q_CUDA_OK(cudaLaunchKernelEx(&cfg, kern, ta, tb, to, tr, p));
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
 
+// tb1: B tensor map with a full [256 x 128B] box (CL = 1); tb2: half box [128 x 128B] for the multicast path (CL = 2)
+struct GemmMaps { CUtensorMap a, b1, b2, out, res; };
+
+static int g_force_cluster = 0;     // 0 = auto, 1 = always CL 1, 2 = always CL 2 (debug/bench knob: b200q_gemm_set_cluster)
+
+template <typename OutT, int EPI, bool W4, int NSTAGE = 4>
+static int launch_gemm(const GemmMaps& m, const GemmParams& p, cudaStream_t st) {
+  const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
+  // pairs only pay off when there is more than one wave of tiles and at least two row blocks
+  bool pair = tiles_m >= 2 && tiles_m * tiles_n >= 2 * sm_count();
+  if (g_force_cluster == 1) pair = false;
+  if (g_force_cluster == 2) pair = tiles_m >= 2;
+  if (pair) return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 2>(m.a, m.b2, m.out, m.res, p, st);
+  return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 1>(m.a, m.b1, m.out, m.res, p, st);
+}
+
 template <typename OutT, bool W4>
-static int dispatch_epi(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to,
-                        const CUtensorMap& tr, const GemmParams& p, cudaStream_t st) {
+static int dispatch_epi(int epi, const GemmMaps& m, const GemmParams& p, cudaStream_t st) {
   switch (epi) {
-    case B200Q_EPI_NONE: return launch_gemm<OutT, B200Q_EPI_NONE, W4>(ta, tb, to, tr, p, st);
-    case B200Q_EPI_GELU_TANH: return launch_gemm<OutT, B200Q_EPI_GELU_TANH, W4>(ta, tb, to, tr, p, st);
+    case B200Q_EPI_NONE: return launch_gemm<OutT, B200Q_EPI_NONE, W4>(m, p, st);
+    case B200Q_EPI_GELU_TANH: return launch_gemm<OutT, B200Q_EPI_GELU_TANH, W4>(m, p, st);
   }
   set_error("gemm: unsupported epilogue %d for this out_dtype", epi);
   return B200Q_ERR_BAD_ARG;
@@ -471,13 +520,18 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
   B200Q_REQUIRE(aligned(out, 16) && (ldo * osz) % 16 == 0, B200Q_ERR_BAD_ARG,
                 "gemm: out must be 16-byte aligned with a 16-byte-multiple row pitch");
 
-  CUtensorMap ta, tb, to, tr;
+  GemmMaps mp;
+  CUtensorMap &ta = mp.a, &to = mp.out, &tr = mp.res;
   int rc;
   if ((rc = make_tmap_2d(&ta, qa, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, M, K, lda, BM, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if (W4) {
-    if ((rc = make_tmap_2d(&tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, kw_bytes, ldw, BN, BK / 2, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
-  } else {
-    if ((rc = make_tmap_2d(&tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, BN, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  for (int half = 0; half < 2; ++half) {
+    CUtensorMap* tb = half ? &mp.b2 : &mp.b1;
+    const int box_rows = half ? BN / 2 : BN;
+    if (W4) {
+      if ((rc = make_tmap_2d(tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, kw_bytes, ldw, box_rows, BK / 2, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+    } else {
+      if ((rc = make_tmap_2d(tb, qw, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, N, K, ldw, box_rows, BK, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+    }
   }
   CUtensorMapDataType odt = out_dtype == B200Q_BF16  ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                             : out_dtype == B200Q_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16
@@ -492,18 +546,21 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
   p.bias = bias; p.bias_dtype = bias_dtype; p.gate = gate; p.epilogue = epilogue;
   p.zp_offset = W4 ? -8 : 0;
 
-  if (raw) return launch_gemm<int32_t, B200Q_EPI_NONE, W4>(ta, tb, to, tr, p, st);
+  if (raw) return launch_gemm<int32_t, B200Q_EPI_NONE, W4>(mp, p, st);
   if (epilogue == B200Q_EPI_GATE_RESIDUAL) {
     B200Q_REQUIRE(out_dtype == B200Q_F32, B200Q_ERR_BAD_ARG, "gemm: gate-residual epilogue writes the fp32 residual stream");
     B200Q_REQUIRE(residual != nullptr, B200Q_ERR_BAD_ARG, "gemm: residual required");
     B200Q_REQUIRE(ldr >= N && aligned(residual, 16) && (ldr * 4) % 16 == 0, B200Q_ERR_BAD_ARG, "gemm: bad residual layout");
     if ((rc = make_tmap_2d(&tr, residual, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, M, N, ldr, 32, 32, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-    return launch_gemm<float, B200Q_EPI_GATE_RESIDUAL, W4>(ta, tb, to, tr, p, st);
+    // short K: the epilogue (8 B/element of HBM traffic) is the bottleneck -> 3 ring stages + prefetched residual boxes;
+    // long K: the main loop dominates -> keep the 4-stage ring
+    if (K < 4096) return launch_gemm<float, B200Q_EPI_GATE_RESIDUAL, W4, 3>(mp, p, st);
+    return launch_gemm<float, B200Q_EPI_GATE_RESIDUAL, W4, 4>(mp, p, st);
   }
   switch (out_dtype) {
-    case B200Q_BF16: return dispatch_epi<__nv_bfloat16, W4>(epilogue, ta, tb, to, tr, p, st);
-    case B200Q_F16: return dispatch_epi<__half, W4>(epilogue, ta, tb, to, tr, p, st);
-    case B200Q_F32: return dispatch_epi<float, W4>(epilogue, ta, tb, to, tr, p, st);
+    case B200Q_BF16: return dispatch_epi<__nv_bfloat16, W4>(epilogue, mp, p, st);
+    case B200Q_F16: return dispatch_epi<__half, W4>(epilogue, mp, p, st);
+    case B200Q_F32: return dispatch_epi<float, W4>(epilogue, mp, p, st);
   }
   return B200Q_ERR_BAD_ARG;
 }
@@ -511,6 +568,12 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
 }  // namespace b200q
 
 using namespace b200q;
+
+extern "C" int b200q_gemm_set_cluster(int mode) {
+  if (mode < 0 || mode > 2) return B200Q_ERR_BAD_ARG;
+  g_force_cluster = mode;
+  return B200Q_OK;
+}
 
 extern "C" int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, int64_t ldw, const float* delta_a,
                                const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias,

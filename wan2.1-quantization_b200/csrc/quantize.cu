@@ -61,21 +61,23 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
   __shared__ int s_sum[32];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rows_per_cta = (blockDim.x >> 5) / warps_per_row;
+  const int rows_per_cta = (THREADS / 32) / warps_per_row;
   const int row_in_cta = warp / warps_per_row;
-  const int wr = warp - row_in_cta * warps_per_row;
-  const int64_t row = (int64_t)blockIdx.x * rows_per_cta + row_in_cta;
-  const bool row_ok = row < a.rows;
+  const int w0 = row_in_cta * warps_per_row;
+  const int wr = warp - w0;
+  const int row = (int)blockIdx.x * rows_per_cta + row_in_cta;          // rows < 2^31 (checked on the host)
+  const bool row_ok = row < (int)a.rows;
   const int tpr = warps_per_row * 32;
   const int t = wr * 32 + lane;
   const int kv = (int)(a.cols / N);
 
-  const T* xrow = reinterpret_cast<const T*>(a.x) + (row_ok ? row : 0) * a.ldx;
+  const T* xrow = reinterpret_cast<const T*>(a.x) + (int64_t)(row_ok ? row : 0) * a.ldx + (int64_t)t * N;
   uint4 raw[V];
+  bool live[V];
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int j = v * tpr + t;
-    raw[v] = (row_ok && j < kv) ? ldg_stream16(xrow + (int64_t)j * N) : make_uint4(0, 0, 0, 0);
+    live[v] = row_ok && (v * tpr + t) < kv;
+    raw[v] = live[v] ? ldg_stream16(xrow + (int64_t)v * tpr * N) : make_uint4(0, 0, 0, 0);
   }
 
   float delta, zp;
@@ -90,14 +92,13 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
     VT::stat_final(st, s0, s1);
     s0 = warp_max(s0);
     if (MODE == kAsymDyn) s1 = warp_min(s1);
-    if (warps_per_row > 1) {
+    if (warps_per_row > 1) {                   // one smem hop; every warp folds the W partials itself (W <= 32 broadcasts)
       if (lane == 0) { s_red[0][warp] = s0; s_red[1][warp] = s1; }
       __syncthreads();
-      const int w0 = row_in_cta * warps_per_row;
-      float r0 = (lane < warps_per_row) ? s_red[0][w0 + lane] : 0.f;
-      float r1 = (lane < warps_per_row) ? s_red[1][w0 + lane] : 0.f;
-      s0 = warp_max(r0);
-      if (MODE == kAsymDyn) s1 = warp_min(r1);
+      for (int i = 0; i < warps_per_row; ++i) {
+        s0 = fmaxf(s0, s_red[0][w0 + i]);
+        if (MODE == kAsymDyn) s1 = fminf(s1, s_red[1][w0 + i]);
+      }
     }
     row_params<MODE>(s0, s1, a, delta, zp);
   }
@@ -106,11 +107,10 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
   const uint64_t r2 = pack_f32x2(r, r), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
   const int zpi = __float2int_rn(zp) + 0x4B400000;      // also strips the magic-number exponent bits
   const int lo = (int)a.clamp_lo, hi = (int)a.clamp_hi;
-  int8_t* qrow = a.q + (row_ok ? row : 0) * a.ldq;
+  int8_t* qrow = a.q + (int64_t)(row_ok ? row : 0) * a.ldq + (int64_t)t * N;
   int sum = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int j = v * tpr + t;
     uint64_t xp[N / 2];
     VT::unpack_pairs(raw[v], xp);
     uint32_t packed[N / 4];
@@ -128,11 +128,12 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
         for (int i = 0; i < 4; ++i) c[i] = (uint32_t)min(max((int)c[i] - zpi, lo), hi);
       }
       packed[g] = pack4((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
-      if (j < kv) sum = __dp4a((int)packed[g], 0x01010101, sum);
+      // dead vectors hold x = 0 -> code 0 for symmetric quantizers; with a zero point they must be masked
+      if (MODE == kSymDyn || live[v]) sum = __dp4a((int)packed[g], 0x01010101, sum);
     }
-    if (row_ok && j < kv) {
-      if (N == 4) stg_stream4(qrow + (int64_t)j * N, packed[0]);
-      else stg_stream8(qrow + (int64_t)j * N, make_uint2(packed[0], packed[N / 4 - 1]));
+    if (live[v]) {
+      if (N == 4) stg_stream4(qrow + (int64_t)v * tpr * N, packed[0]);
+      else stg_stream8(qrow + (int64_t)v * tpr * N, make_uint2(packed[0], packed[N / 4 - 1]));
     }
   }
 
@@ -141,9 +142,10 @@ __global__ void __launch_bounds__(THREADS) quant_rows_kernel(const QuantArgs a, 
     if (warps_per_row > 1) {
       if (lane == 0) s_sum[warp] = sum;
       __syncthreads();
-      const int w0 = row_in_cta * warps_per_row;
-      int r0 = (lane < warps_per_row) ? s_sum[w0 + lane] : 0;
-      sum = warp_sum(r0);
+      if (t == 0) {
+        sum = 0;
+        for (int i = 0; i < warps_per_row; ++i) sum += s_sum[w0 + i];
+      }
     }
     if (row_ok && t == 0) a.rowsum[row] = sum;
   }
@@ -211,33 +213,26 @@ static int launch_quant(const QuantArgs& a, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   const bool fast = (a.cols % N == 0) && (a.ldx % N == 0) && aligned(a.x, 16) &&
                     (a.ldq % (N == 4 ? 4 : 8) == 0) && aligned(a.q, N == 4 ? 4 : 8) &&
-                    (a.cols / N <= 8 * 32 * 32);
+                    (a.cols / N <= 8 * 32 * 32);   // <= 8 vectors per thread of a 1024-thread CTA
   if (!fast) {
     quant_rows_generic_kernel<T, MODE><<<(unsigned)a.rows, 256, 0, st>>>(a);
     B200Q_CHECK_LAUNCH();
     return B200Q_OK;
   }
   const int kv = (int)(a.cols / N);
-  int W = 1;
-  while (W < 8 && (kv + 32 * W - 1) / (32 * W) > 8) W *= 2;
-  int threads = 256;
-  if ((kv + 32 * W - 1) / (32 * W) > 8) { W = 32; threads = 1024; }
-  const int V = (kv + 32 * W - 1) / (32 * W);
-  const int rows_per_cta = (threads / 32) / W;
+  const RowLayout lay = pick_row_layout(kv, N == 4 ? 12 : 10);       // 48 / 40 data registers per thread
+  const int W = lay.W, V = lay.V;
+  const int rows_per_cta = (lay.threads / 32) / W;
   const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
-#define B200Q_LAUNCH_V(VV) quant_rows_kernel<T, VV, MODE, 256><<<grid, 256, 0, st>>>(a, W)
-  if (threads == 1024) {      // very long rows: one 1024-thread CTA per row
+  if (lay.threads == 1024) {      // very long rows: one 1024-thread CTA per row
     if (V <= 4) quant_rows_kernel<T, 4, MODE, 1024><<<grid, 1024, 0, st>>>(a, W);
-    else quant_rows_kernel<T, 8, MODE, 1024><<<grid, 1024, 0, st>>>(a, W);
-  } else if (V <= 1) B200Q_LAUNCH_V(1);
-  else if (V <= 2) B200Q_LAUNCH_V(2);
-  else if (V <= 3) B200Q_LAUNCH_V(3);
-  else if (V <= 4) B200Q_LAUNCH_V(4);
-  else if (V <= 5) B200Q_LAUNCH_V(5);
-  else if (V <= 6) B200Q_LAUNCH_V(6);
-  else if (V <= 7) B200Q_LAUNCH_V(7);
-  else B200Q_LAUNCH_V(8);
+    else if (V <= 8) quant_rows_kernel<T, 8, MODE, 1024><<<grid, 1024, 0, st>>>(a, W);
+    else { set_error("quant_rows: internal layout error"); return B200Q_ERR_UNSUPPORTED; }
+  } else {
+#define B200Q_LAUNCH_V(VV) quant_rows_kernel<T, VV, MODE, 256><<<grid, 256, 0, st>>>(a, W)
+    B200Q_DISPATCH_V(V, B200Q_LAUNCH_V);
 #undef B200Q_LAUNCH_V
+  }
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
