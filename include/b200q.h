@@ -132,7 +132,8 @@ B200Q_API int b200q_gemm_w8a8(const int8_t* qa, int64_t lda, const int8_t* qw, i
                     b200q_stream_t stream);
 
 /* Tile-scheduling knob for both GEMMs (debug / benchmarking): 0 = automatic (default), 1 = single-CTA tiles only,
- * 2 = 2-CTA clusters with TMA-multicast B tiles whenever the problem has >= 2 row blocks.  Results are identical. */
+ * 2 = 2-CTA clusters with TMA-multicast B tiles whenever the problem has >= 2 row blocks, 3 = 2-CTA clusters issuing
+ * tcgen05.mma.cta_group::2 (M = 256 across the pair).  Results are identical. */
 B200Q_API int b200q_gemm_set_cluster(int mode);
 
 /* codes int8 [N,K] in [-8,7] -> packed uint8 [N, ceil(K/8)*4].  Format (consumed by b200q_gemm_w4a8's in-smem

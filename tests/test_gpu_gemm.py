@@ -207,12 +207,13 @@ def test_w4a8_gelu_and_gate_epilogues(dev):
 
 
 # ---- 2-CTA cluster / TMA-multicast scheduling: identical results ----------------------------------------------
+@pytest.mark.parametrize("mode", [2, 3])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 128), (384, 512, 1536), (130, 272, 144), (1000, 1536, 512), (129, 8, 16)])
-def test_cluster_multicast_bit_exact(dev, M, N, K):
+def test_cluster_modes_bit_exact(dev, M, N, K, mode):
     qa, qw = _codes(M, K, M + K + 5), _codes(N, K, N + K + 6, -128, 127)
     ref = O.int_accumulators(qa, qw)
     try:
-        b200q.gemm_set_cluster(2)
+        b200q.gemm_set_cluster(mode)
         acc = b200q.gemm_w8a8(qa.to(dev), qw.to(dev), out_dtype=torch.int32)
         assert torch.equal(acc.cpu(), ref)
         # W4 converters + remote barrier arrives

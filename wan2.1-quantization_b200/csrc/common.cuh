@@ -110,6 +110,9 @@ __device__ __forceinline__ uint64_t pack_u32x2(uint32_t a, uint32_t b) {
 __device__ __forceinline__ void unpack_u32x2(uint64_t v, uint32_t& a, uint32_t& b) {
   asm("mov.b64 {%0, %1}, %2;" : "=r"(a), "=r"(b) : "l"(v));
 }
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& a, float& b) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+}
 __device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
   uint64_t d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));

@@ -8,6 +8,8 @@
 //                       hidden/4 threads and cannot launch for hidden > 4096).
 //  b200q_gate_residual: out = residual + y*gate (model.py:337,362; reference fused.cu:382-483).
 #include "common.cuh"
+#include <type_traits>
+#include <stdlib.h>
 
 namespace b200q {
 
@@ -55,10 +57,14 @@ __device__ __forceinline__ float row_reduce_max(float v, float* s_slot, int warp
   return v;
 }
 
-template <typename T, typename YT, int V, int THREADS>
+// MODE bit 0: LayerNorm affine (ln_w, ln_b) ; bit 1: adaLN modulate (scale, shift).  Compile-time so the inner loops
+// carry no per-element selects.  All element math is packed fp32x2 (FADD2 / FMUL2 / FFMA2).
+template <typename T, typename YT, int V, int THREADS, int MODE>
 __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, const int warps_per_row) {
   using VT = Vec16<T>;
   constexpr int N = VT::N;
+  constexpr int P = N / 2;
+  constexpr bool AFFINE = (MODE & 1) != 0, MOD = (MODE & 2) != 0;
   __shared__ float s_buf[3][32];
   __shared__ int s_sum[32];
 
@@ -67,74 +73,85 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   const int row_in_cta = warp / warps_per_row;
   const int w0 = row_in_cta * warps_per_row;
   const int wr = warp - w0;
-  const int64_t row = (int64_t)blockIdx.x * rows_per_cta + row_in_cta;
-  const bool row_ok = row < a.rows;
+  const int row = (int)blockIdx.x * rows_per_cta + row_in_cta;
+  const bool row_ok = row < (int)a.rows;
   const int tpr = warps_per_row * 32;
   const int t = wr * 32 + lane;
   const int kv = (int)(a.cols / N);
   const float inv_c = 1.f / (float)a.cols;
 
-  const T* xrow = reinterpret_cast<const T*>(a.x) + (row_ok ? row : 0) * a.ldx;
-  float f[V][N];
-  float s = 0.f;
+  const T* xrow = reinterpret_cast<const T*>(a.x) + (int64_t)(row_ok ? row : 0) * a.ldx + (int64_t)t * N;
+  uint64_t x[V][P];
+  bool live[V];
+  uint64_t acc2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int j = v * tpr + t;
-    const uint4 raw = (row_ok && j < kv) ? ldg_stream16(xrow + (int64_t)j * N) : make_uint4(0, 0, 0, 0);
-    VT::unpack(raw, f[v]);
+    live[v] = row_ok && (v * tpr + t) < kv;
+    const uint4 raw = live[v] ? ldg_stream16(xrow + (int64_t)v * tpr * N) : make_uint4(0, 0, 0, 0);
+    VT::unpack_pairs(raw, x[v]);
 #pragma unroll
-    for (int i = 0; i < N; ++i) s += f[v][i];
+    for (int i = 0; i < P; ++i) acc2 = add_f32x2(acc2, x[v][i]);
   }
-  const float mean = row_reduce_sum(s, s_buf[0], warp, lane, w0, warps_per_row) * inv_c;
-  float ss = 0.f;
+  float s_lo, s_hi;
+  unpack_f32x2(acc2, s_lo, s_hi);
+  const float mean = row_reduce_sum(s_lo + s_hi, s_buf[0], warp, lane, w0, warps_per_row) * inv_c;
+  const uint64_t nmean2 = pack_f32x2(-mean, -mean);
+  uint64_t ss2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const bool live = (v * tpr + t) < kv;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const float d = f[v][i] - mean;
-      ss += live ? d * d : 0.f;
+    for (int i = 0; i < P; ++i) {
+      x[v][i] = live[v] ? add_f32x2(x[v][i], nmean2) : pack_f32x2(0.f, 0.f);       // d = x - mean (0 for padding lanes)
+      ss2 = fma_f32x2(x[v][i], x[v][i], ss2);
     }
   }
-  const float var = row_reduce_sum(ss, s_buf[1], warp, lane, w0, warps_per_row) * inv_c;
+  unpack_f32x2(ss2, s_lo, s_hi);
+  const float var = row_reduce_sum(s_lo + s_hi, s_buf[1], warp, lane, w0, warps_per_row) * inv_c;
   const float rstd = __frsqrt_rn(var + a.eps);
+  const uint64_t rstd2 = pack_f32x2(rstd, rstd), one2 = pack_f32x2(1.f, 1.f);
 
   float amax = 0.f;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int j = v * tpr + t;
-    const bool live = j < kv;
-    const int c0 = j * N;
-    // per-channel vectors as 16-byte loads (L1/L2 resident: cols*4 bytes, shared by every row)
-    float pw[N], pb[N], psc[N], psh[N];
+    const int c0 = live[v] ? (v * tpr + t) * N : 0;
 #pragma unroll
     for (int h = 0; h < N / 4; ++h) {
-      const int c = live ? c0 + 4 * h : 0;
-      const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
-      const float4 w4 = a.ln_w ? __ldg(reinterpret_cast<const float4*>(a.ln_w + c)) : one;
-      const float4 b4 = a.ln_b ? __ldg(reinterpret_cast<const float4*>(a.ln_b + c)) : zero;
-      const float4 s4 = a.scale ? __ldg(reinterpret_cast<const float4*>(a.scale + c)) : zero;
-      const float4 h4 = a.shift ? __ldg(reinterpret_cast<const float4*>(a.shift + c)) : zero;
-      pw[4 * h] = w4.x; pw[4 * h + 1] = w4.y; pw[4 * h + 2] = w4.z; pw[4 * h + 3] = w4.w;
-      pb[4 * h] = b4.x; pb[4 * h + 1] = b4.y; pb[4 * h + 2] = b4.z; pb[4 * h + 3] = b4.w;
-      psc[4 * h] = s4.x; psc[4 * h + 1] = s4.y; psc[4 * h + 2] = s4.z; psc[4 * h + 3] = s4.w;
-      psh[4 * h] = h4.x; psh[4 * h + 1] = h4.y; psh[4 * h + 2] = h4.z; psh[4 * h + 3] = h4.w;
+      uint64_t y0 = mul_f32x2(x[v][2 * h], rstd2), y1 = mul_f32x2(x[v][2 * h + 1], rstd2);
+      if (AFFINE) {
+        const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.ln_w + c0 + 4 * h));
+        const float4 b4 = __ldg(reinterpret_cast<const float4*>(a.ln_b + c0 + 4 * h));
+        y0 = add_f32x2(mul_f32x2(y0, pack_f32x2(w4.x, w4.y)), pack_f32x2(b4.x, b4.y));
+        y1 = add_f32x2(mul_f32x2(y1, pack_f32x2(w4.z, w4.w)), pack_f32x2(b4.z, b4.w));
+      }
+      if (MOD) {      // ln*(1+e1) + e0, two roundings like the reference's separate ops (model.py:327)
+        const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.scale + c0 + 4 * h));
+        const float4 h4 = __ldg(reinterpret_cast<const float4*>(a.shift + c0 + 4 * h));
+        y0 = add_f32x2(mul_f32x2(y0, add_f32x2(one2, pack_f32x2(s4.x, s4.y))), pack_f32x2(h4.x, h4.y));
+        y1 = add_f32x2(mul_f32x2(y1, add_f32x2(one2, pack_f32x2(s4.z, s4.w))), pack_f32x2(h4.z, h4.w));
+      }
+      if (!live[v]) { y0 = pack_f32x2(0.f, 0.f); y1 = y0; }
+      x[v][2 * h] = y0; x[v][2 * h + 1] = y1;
+      float f0, f1, f2, f3;
+      unpack_f32x2(y0, f0, f1); unpack_f32x2(y1, f2, f3);
+      amax = fmaxf(fmaxf(fabsf(f0), fabsf(f1)), amax);
+      amax = fmaxf(fmaxf(fabsf(f2), fabsf(f3)), amax);
     }
+    if (a.y_out != nullptr && live[v]) {
+      YT* yrow = reinterpret_cast<YT*>(a.y_out) + (int64_t)row * a.ldy + c0;
+      float f[N];
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      float y = (f[v][i] - mean) * rstd;
-      if (a.ln_w) y = __fmul_rn(y, pw[i]);
-      if (a.ln_b) y = __fadd_rn(y, pb[i]);
-      if (a.scale) y = __fmul_rn(y, __fadd_rn(1.f, psc[i]));   // ln*(1+e1)   model.py:327
-      if (a.shift) y = __fadd_rn(y, psh[i]);                   //  + e0
-      y = live ? y : 0.f;
-      f[v][i] = y;
-      amax = fmaxf(amax, fabsf(y));
-    }
-    if (a.y_out != nullptr && row_ok && live) {
-      YT* yrow = reinterpret_cast<YT*>(a.y_out) + row * a.ldy + c0;
+      for (int i = 0; i < P; ++i) unpack_f32x2(x[v][i], f[2 * i], f[2 * i + 1]);
+      if constexpr (sizeof(YT) == 4) {
 #pragma unroll
-      for (int i = 0; i < N; ++i) yrow[i] = from_f32<YT>(f[v][i]);
+        for (int h = 0; h < N / 4; ++h)
+          *reinterpret_cast<float4*>(yrow + 4 * h) = make_float4(f[4 * h], f[4 * h + 1], f[4 * h + 2], f[4 * h + 3]);
+      } else {
+        __nv_bfloat162 o[P];
+#pragma unroll
+        for (int i = 0; i < P; ++i) o[i] = __floats2bfloat162_rn(f[2 * i], f[2 * i + 1]);
+        if (N == 8) *reinterpret_cast<uint4*>(yrow) = *reinterpret_cast<uint4*>(o);
+        else *reinterpret_cast<uint2*>(yrow) = *reinterpret_cast<uint2*>(o);
+      }
     }
   }
   if (a.q == nullptr) return;       // uniform across the CTA
@@ -144,26 +161,25 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   if (delta < 1.0e-6f) delta = 1.0e-6f;                                   // base_quantizer.py:122-128
   const float r = __frcp_rn(delta);
   const uint64_t r2 = pack_f32x2(r, r), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
-  int8_t* qrow = a.q + (row_ok ? row : 0) * a.ldq;
+  int8_t* qrow = a.q + (int64_t)(row_ok ? row : 0) * a.ldq + (int64_t)t * N;
   int sum = 0;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int j = v * tpr + t;
     uint32_t packed[N / 4];
 #pragma unroll
     for (int g = 0; g < N / 4; ++g) {
       uint32_t c[4];
 #pragma unroll
       for (int i = 0; i < 2; ++i) {
-        const uint64_t qb = div_rn_hoisted_rne2(pack_f32x2(f[v][4 * g + 2 * i], f[v][4 * g + 2 * i + 1]), nd2, r2, magic2);
+        const uint64_t qb = div_rn_hoisted_rne2(x[v][2 * g + i], nd2, r2, magic2);
         unpack_u32x2(qb, c[2 * i], c[2 * i + 1]);
       }
       packed[g] = pack4i((int)c[0], (int)c[1], (int)c[2], (int)c[3]);
       sum = __dp4a((int)packed[g], 0x01010101, sum);
     }
-    if (row_ok && j < kv) {
-      if (N == 4) stg_stream4(qrow + (int64_t)j * N, packed[0]);
-      else stg_stream8(qrow + (int64_t)j * N, make_uint2(packed[0], packed[N / 4 - 1]));
+    if (live[v]) {
+      if (N == 4) stg_stream4(qrow + (int64_t)v * tpr * N, packed[0]);
+      else stg_stream8(qrow + (int64_t)v * tpr * N, make_uint2(packed[0], packed[N / 4 - 1]));
     }
   }
   if (a.rowsum != nullptr) {
@@ -181,26 +197,37 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   if (row_ok && t == 0) a.delta[row] = delta;
 }
 
-template <typename T, typename YT>
-static int launch_ln(const LnArgs& a, cudaStream_t st) {
+template <typename T, typename YT, int MODE>
+static int launch_ln_mode(const LnArgs& a, cudaStream_t st) {
   constexpr int N = Vec16<T>::N;
   const int kv = (int)(a.cols / N);
-  const RowLayout lay = pick_row_layout(kv, N == 4 ? 12 : 6);        // fp32 values live in registers: 48 per thread
+  static int vmax_env = -1;          // tuning knob (B200Q_LN_VMAX): vectors per thread before a row is split over more warps
+  if (vmax_env < 0) { const char* e = getenv("B200Q_LN_VMAX"); vmax_env = e ? atoi(e) : 0; }
+  const int vmax = vmax_env > 0 ? (N == 4 ? vmax_env : (vmax_env + 1) / 2) : (N == 4 ? 12 : 6);
+  const RowLayout lay = pick_row_layout(kv, vmax);                    // fp32 values live in registers: <= 48 per thread
   const int W = lay.W, V = lay.V;
   B200Q_REQUIRE(V <= 12 && (lay.threads == 256 || V <= 8), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: cols=%lld too large",
                 (long long)a.cols);
   const int rows_per_cta = (lay.threads / 32) / W;
   const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
-  if (lay.threads == 1024) {
-    if (V <= 4) ln_mod_quant_kernel<T, YT, 4, 1024><<<grid, 1024, 0, st>>>(a, W);
-    else ln_mod_quant_kernel<T, YT, 8, 1024><<<grid, 1024, 0, st>>>(a, W);
-  } else {
-#define B200Q_LN(VV) ln_mod_quant_kernel<T, YT, VV, 256><<<grid, 256, 0, st>>>(a, W)
-    B200Q_DISPATCH_V(V, B200Q_LN);
-#undef B200Q_LN
-  }
+  if (lay.threads == 1024) ln_mod_quant_kernel<T, YT, 8, 1024, MODE><<<grid, 1024, 0, st>>>(a, W);
+  else if (V <= 2) ln_mod_quant_kernel<T, YT, 2, 256, MODE><<<grid, 256, 0, st>>>(a, W);
+  else if (V <= 4) ln_mod_quant_kernel<T, YT, 4, 256, MODE><<<grid, 256, 0, st>>>(a, W);
+  else if (V <= 8) ln_mod_quant_kernel<T, YT, 8, 256, MODE><<<grid, 256, 0, st>>>(a, W);
+  else ln_mod_quant_kernel<T, YT, 12, 256, MODE><<<grid, 256, 0, st>>>(a, W);
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
+}
+
+template <typename T, typename YT>
+static int launch_ln(const LnArgs& a, cudaStream_t st) {
+  const int mode = ((a.ln_w || a.ln_b) ? 1 : 0) | ((a.scale || a.shift) ? 2 : 0);
+  switch (mode) {
+    case 0: return launch_ln_mode<T, YT, 0>(a, st);
+    case 1: return launch_ln_mode<T, YT, 1>(a, st);
+    case 2: return launch_ln_mode<T, YT, 2>(a, st);
+    default: return launch_ln_mode<T, YT, 3>(a, st);
+  }
 }
 
 // ---- RMSNorm over the full model dim + 3-axis RoPE --------------------------------------------
@@ -260,7 +287,19 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
       const float4 w4 = __ldg(reinterpret_cast<const float4*>(a.weight + c0 + 4 * h));
       const float wv[4] = {w4.x, w4.y, w4.z, w4.w};
 #pragma unroll
-      for (int i = 0; i < 4; ++i) y[4 * h + i] = to_f32(from_f32<T>(f[v][4 * h + i] * rstd)) * wv[i];   // .type_as(x) * weight
+      for (int i = 0; i < 4; i += 2) {                       // .type_as(x) * weight: round to x's 16-bit type, back to fp32
+        const float u0 = f[v][4 * h + i] * rstd, u1 = f[v][4 * h + i + 1] * rstd;
+        float r0, r1;
+        if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+          const __nv_bfloat162 pk = __floats2bfloat162_rn(u0, u1);          // one F2FP, then two shifts
+          const uint32_t w = *reinterpret_cast<const uint32_t*>(&pk);
+          r0 = __uint_as_float(w << 16); r1 = __uint_as_float(w & 0xffff0000u);
+        } else {
+          const float2 t2 = __half22float2(__floats2half2_rn(u0, u1));
+          r0 = t2.x; r1 = t2.y;
+        }
+        y[4 * h + i] = r0 * wv[i]; y[4 * h + i + 1] = r1 * wv[i + 1];
+      }
     }
     if (a.cos_t != nullptr) {
       const int p0 = (c0 % a.head_dim) >> 1;                 // first pair index inside the head (multiple of 4)
@@ -383,9 +422,13 @@ extern "C" int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int6
   B200Q_REQUIRE(cols % vecn == 0 && ldx % vecn == 0 && aligned(x, 16), B200Q_ERR_UNSUPPORTED,
                 "ln_mod_quant: cols and ldx must be multiples of %d and x 16-byte aligned", vecn);
   B200Q_REQUIRE(q == nullptr || (ldq % vecn == 0 && aligned(q, vecn)), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: q misaligned");
+  B200Q_REQUIRE(y_out == nullptr || (ldy % vecn == 0 && aligned(y_out, 16)), B200Q_ERR_UNSUPPORTED, "ln_mod_quant: y_out misaligned");
   B200Q_REQUIRE((!ln_w || aligned(ln_w, 16)) && (!ln_b || aligned(ln_b, 16)) && (!shift || aligned(shift, 16)) &&
                     (!scale || aligned(scale, 16)),
                 B200Q_ERR_BAD_ARG, "ln_mod_quant: per-channel vectors must be 16-byte aligned");
+  B200Q_REQUIRE((ln_w == nullptr) == (ln_b == nullptr) && (scale == nullptr) == (shift == nullptr), B200Q_ERR_BAD_ARG,
+                "ln_mod_quant: ln_w/ln_b and scale/shift are given in pairs");
+  B200Q_REQUIRE(rows <= 0x7fffffff, B200Q_ERR_UNSUPPORTED, "ln_mod_quant: rows > 2^31-1");
   LnArgs a{};
   a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.ln_w = ln_w; a.ln_b = ln_b; a.eps = eps;
   a.shift = shift; a.scale = scale; a.n_levels = (float)((1 << (n_bits - 1)) - 1);
@@ -395,16 +438,14 @@ extern "C" int b200q_ln_mod_quant(const void* x, int x_dtype, int64_t rows, int6
   switch (y_out ? y_dtype : B200Q_F32) {                                               \
     case B200Q_F32: return launch_ln<T, float>(a, st);                                 \
     case B200Q_BF16: return launch_ln<T, __nv_bfloat16>(a, st);                        \
-    case B200Q_F16: return launch_ln<T, __half>(a, st);                                \
-    default: set_error("ln_mod_quant: bad y_dtype %d", y_dtype); return B200Q_ERR_BAD_ARG; \
+    default: set_error("ln_mod_quant: y_dtype must be f32 or bf16"); return B200Q_ERR_BAD_ARG; \
   }
   switch (x_dtype) {
     case B200Q_F32: B200Q_LN_Y(float)
     case B200Q_BF16: B200Q_LN_Y(__nv_bfloat16)
-    case B200Q_F16: B200Q_LN_Y(__half)
   }
 #undef B200Q_LN_Y
-  set_error("ln_mod_quant: bad x_dtype %d", x_dtype);
+  set_error("ln_mod_quant: x_dtype must be f32 or bf16 (got %d)", x_dtype);
   return B200Q_ERR_BAD_ARG;
 }
 

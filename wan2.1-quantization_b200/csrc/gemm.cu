@@ -40,15 +40,21 @@ constexpr int TMEM_COLS = 512;
 //       of two 32 KB SWIZZLE_128B int8 tiles that the MMA reads.
 // The gate-residual epilogue (8 B/element of HBM traffic: memory-bound) trades one ring stage for a second staging
 // buffer per epilogue warp so the residual box of chunk u+1 is in flight while chunk u is processed.
-template <bool W4, int NSTAGE>
+// PAIR: 0 = single CTA per tile; 1 = 2-CTA cluster, single-CTA MMAs, B tile multicast; 2 = 2-CTA cluster with
+// tcgen05.mma.cta_group::2 (M = 256 across the pair): each CTA stages only HALF of the B tile, so the smem traffic per
+// MMA (operand fill + operand read) drops by a third and two more ring stages fit.
+template <bool W4, int NSTAGE, int PAIR>
 struct GemmSmem {
-  static constexpr int stages = NSTAGE;                      // 4, or 3 with double-buffered staging (short-K gate-residual)
+  static constexpr bool mma2 = (PAIR == 2);
+  static constexpr int stages = mma2 ? NSTAGE + 2 : NSTAGE;   // NSTAGE 4 (or 3 with double-buffered staging: short-K gate-residual)
   static constexpr int staging_bufs = (NSTAGE == 3) ? 2 : 1;
-  static constexpr int b_stage = W4 ? B_BYTES / 2 : B_BYTES;
+  static constexpr int b_rows = mma2 ? BN / 2 : BN;            // B rows staged per CTA
+  static constexpr int b_unpacked = b_rows * BK;
+  static constexpr int b_stage = W4 ? b_unpacked / 2 : b_unpacked;
   static constexpr int stage = A_BYTES + b_stage;
   static constexpr int ring = 0;
   static constexpr int unpack = stages * stage;
-  static constexpr int staging = unpack + (W4 ? UNPACK_BUFS * B_BYTES : 0);
+  static constexpr int staging = unpack + (W4 ? UNPACK_BUFS * b_unpacked : 0);
   static constexpr int colparams = staging + EPI_WARPS * staging_bufs * STAGING_BYTES;   // dw[BN] f32, bias[BN] f32, zp[BN] i16
   static constexpr int barriers = colparams + BN * 4 + BN * 4 + BN * 2;
   static constexpr int total = barriers + 256;
@@ -112,8 +118,8 @@ __device__ __forceinline__ uint4 pack_chunk(const float* y) {
 // CL = CTAs per cluster (1 or 2).  CL == 2: the two CTAs of a cluster work on vertically adjacent tiles (same n0);
 // each loads its own A tile and HALF of the shared B tile, multicast into both CTAs' smem, which cuts the L2->SM
 // operand traffic per tile from 48 KB to 32 KB per K-block (the int8 MMA rate is L2-bandwidth-bound at 128x256 tiles).
-template <typename OutT, int EPI, bool W4, int NSTAGE, int CL>
-__global__ void __launch_bounds__(GemmSmem<W4, NSTAGE>::threads, 1)
+template <typename OutT, int EPI, bool W4, int NSTAGE, int PAIR>
+__global__ void __launch_bounds__(GemmSmem<W4, NSTAGE, PAIR>::threads, 1)
 gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                  const GemmParams p) {
@@ -122,9 +128,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
     __trap();
   }
-  using SM = GemmSmem<W4, NSTAGE>;
+  using SM = GemmSmem<W4, NSTAGE, PAIR>;
   constexpr int STAGE_BYTES = SM::stage;
   constexpr int STAGES = SM::stages;
+  constexpr int CL = PAIR ? 2 : 1;
+  constexpr bool MMA2 = SM::mma2;
+  constexpr int UNPACK_BYTES = SM::b_unpacked;
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SM::barriers);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
@@ -150,10 +159,17 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_init(&full_bar[s], 1);
       // a ring slot is free when every MMA warp (and, for W4, every converter warp) of the CLUSTER is done with it:
       // with CL == 2 the peer multicasts half of B into this CTA's slot
-      mbar_init(&empty_bar[s], CL * (W4 ? 1 + CVT_WARPS : 1));
+      // MMA2: one MMA issuer (the leader) releases both CTAs' slots; each CTA's converters release their own packed tile
+      mbar_init(&empty_bar[s], MMA2 ? (W4 ? 1 + CVT_WARPS : 1) : CL * (W4 ? 1 + CVT_WARPS : 1));
     }
-    for (int s = 0; s < UNPACK_BUFS; ++s) { mbar_init(&bready_bar[s], CVT_WARPS); mbar_init(&bfree_bar[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full_bar[s], 1); mbar_init(&tmem_empty_bar[s], EPI_WARPS); }
+    for (int s = 0; s < UNPACK_BUFS; ++s) {
+      mbar_init(&bready_bar[s], MMA2 ? 2 * CVT_WARPS : CVT_WARPS);   // MMA2: the leader waits for both CTAs' converters
+      mbar_init(&bfree_bar[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tmem_full_bar[s], 1);
+      mbar_init(&tmem_empty_bar[s], MMA2 ? 2 * EPI_WARPS : EPI_WARPS);   // MMA2: both CTAs' epilogues drain before the leader reuses TMEM
+    }
     for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
@@ -161,7 +177,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     prefetch_tmap(&tm_a); prefetch_tmap(&tm_b); prefetch_tmap(&tm_out);
     if (EPI == B200Q_EPI_GATE_RESIDUAL) prefetch_tmap(&tm_res);
   }
-  if (warp == 2) tmem_alloc<TMEM_COLS>(tmem_base_slot);
+  if (warp == 2) { if (MMA2) tmem_alloc_2sm<TMEM_COLS>(tmem_base_slot); else tmem_alloc<TMEM_COLS>(tmem_base_slot); }
   tcgen05_fence_before();
   __syncthreads();
   if (CL == 2) cluster_sync();                                 // peer's barriers are initialised before anyone signals them
@@ -177,6 +193,23 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         for (int kb = 0; kb < num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + SM::ring + stage * STAGE_BYTES;
+          if (MMA2) {
+            // both CTAs stage their A rows and their half of B locally.  The leader issues the pair's MMAs, so operand
+            // bytes the tensor core reads directly are credited to the LEADER's barrier; a packed W4 tile is consumed by
+            // the local converter warps first and is credited to the local barrier.
+            const uint32_t lead_bar = mapa_u32(&full_bar[stage], 0);
+            if (W4) {
+              mbar_expect_tx(&full_bar[stage], cta_rank == 0 ? 2 * A_BYTES + SM::b_stage : SM::b_stage);
+              tma_load_2d_2sm(sa, &tm_a, lead_bar, kb * BK, m0);
+              tma_load_2d(sa + A_BYTES, &tm_b, &full_bar[stage], kb * (BK / 2), n0 + cta_rank * (BN / 2));
+            } else {
+              if (cta_rank == 0) mbar_expect_tx(&full_bar[stage], 2 * STAGE_BYTES);
+              tma_load_2d_2sm(sa, &tm_a, lead_bar, kb * BK, m0);
+              tma_load_2d_2sm(sa + A_BYTES, &tm_b, lead_bar, kb * BK, n0 + cta_rank * (BN / 2));
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_expect_tx(&full_bar[stage], STAGE_BYTES);       // own A + both halves of B (one arrives from the peer)
           tma_load_2d(sa, &tm_a, &full_bar[stage], kb * BK, m0);
           if (CL == 2) {
@@ -191,8 +224,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_i8_idesc(BM, BN);
+    if (lane == 0 && (!MMA2 || cta_rank == 0)) {
+      constexpr uint32_t idesc = make_i8_idesc(MMA2 ? 2 * BM : BM, BN);
       int stage = 0; uint32_t phase = 0; int it = 0;
       int ub = 0; uint32_t uphase = 0;
       for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
@@ -206,20 +239,27 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           tcgen05_fence_after();
           const uint32_t sa = smem_u32(smem + SM::ring + stage * STAGE_BYTES);
           const uint64_t adesc = make_kmajor_sw128_desc(sa);
-          const uint64_t bdesc = make_kmajor_sw128_desc(W4 ? smem_u32(smem + SM::unpack + ub * B_BYTES) : sa + A_BYTES);
+          const uint64_t bdesc = make_kmajor_sw128_desc(W4 ? smem_u32(smem + SM::unpack + ub * UNPACK_BYTES) : sa + A_BYTES);
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance both descriptors by k*32 bytes inside the 128B swizzle row (address field is >>4)
-            mma_i8_ss(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc,
-                      (kb | k) != 0 ? 1u : 0u);
+            if (MMA2) mma_i8_ss_2sm(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc,
+                                    (kb | k) != 0 ? 1u : 0u);
+            else mma_i8_ss(tmem_d, adesc + (uint64_t)(k * (UMMA_K >> 4)), bdesc + (uint64_t)(k * (UMMA_K >> 4)), idesc,
+                           (kb | k) != 0 ? 1u : 0u);
           }
-          if (CL == 2) mma_commit_mc(&empty_bar[stage], kAllCtas);   // releases the slot in BOTH CTAs
+          if (MMA2) mma_commit_2sm_mc(&empty_bar[stage], kAllCtas);
+          else if (CL == 2) mma_commit_mc(&empty_bar[stage], kAllCtas);   // releases the slot in BOTH CTAs
           else mma_commit(&empty_bar[stage]);                // slot free once these MMAs have read it
           if (W4) {
-            mma_commit(&bfree_bar[ub]);
+            if (MMA2) mma_commit_2sm_mc(&bfree_bar[ub], kAllCtas);
+            else mma_commit(&bfree_bar[ub]);
             if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
           }
-          if (kb == num_kb - 1) mma_commit(&tmem_full_bar[as]);
+          if (kb == num_kb - 1) {
+            if (MMA2) mma_commit_2sm_mc(&tmem_full_bar[as], kAllCtas);   // accumulator ready in both CTAs' TMEM
+            else mma_commit(&tmem_full_bar[as]);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -235,10 +275,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       for (int kb = 0; kb < num_kb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         mbar_wait(&bfree_bar[ub], uphase ^ 1);
-        const uint8_t* src = smem + SM::ring + stage * STAGE_BYTES + A_BYTES;     // [256 rows][64 B]
-        uint8_t* dst = smem + SM::unpack + ub * B_BYTES;                           // [256 rows][128 B] swizzled
+        const uint8_t* src = smem + SM::ring + stage * STAGE_BYTES + A_BYTES;     // [b_rows][64 B]
+        uint8_t* dst = smem + SM::unpack + ub * UNPACK_BYTES;                      // [b_rows][128 B] swizzled
 #pragma unroll
-        for (int i = 0; i < (BN * 4) / (CVT_WARPS * 32); ++i) {
+        for (int i = 0; i < (SM::b_rows * 4) / (CVT_WARPS * 32); ++i) {
           const int ci = i * (CVT_WARPS * 32) + ct;       // 16-byte packed chunk index: row = ci/4, j = ci%4
           const int r = ci >> 2, j = ci & 3;
           const uint4 w = *reinterpret_cast<const uint4*>(src + ci * 16);
@@ -252,9 +292,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
         fence_proxy_async_smem();                          // generic-proxy writes -> visible to the tensor core (async proxy)
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(&bready_bar[ub]);
+          if (MMA2 && cta_rank != 0) mbar_arrive_remote(&bready_bar[ub], 0);   // the leader issues the pair's MMAs
+          else mbar_arrive(&bready_bar[ub]);
           mbar_arrive(&empty_bar[stage]);                  // this warp is done reading the packed tile
-          if (CL == 2) mbar_arrive_remote(&empty_bar[stage], cta_rank ^ 1);   // ... which the peer half-fills
+          if (CL == 2 && !MMA2) mbar_arrive_remote(&empty_bar[stage], cta_rank ^ 1);   // ... which the peer half-fills
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
         if (++ub == UNPACK_BUFS) { ub = 0; uphase ^= 1; }
@@ -340,7 +381,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (u == CHUNKS - 1 && h == CPS / 32 - 1) {        // accumulator fully read: hand TMEM back to the MMA warp
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty_bar[as]);
+            if (lane == 0) {
+              if (MMA2 && cta_rank != 0) mbar_arrive_remote(&tmem_empty_bar[as], 0);   // the leader owns the MMA schedule
+              else mbar_arrive(&tmem_empty_bar[as]);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 32 / ELEMS; ++c) {             // 16-byte chunks of this thread's row
@@ -400,7 +444,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   __syncthreads();
   if (CL == 2) cluster_sync();                                 // the peer may still signal this CTA's barriers / fill its smem
   tcgen05_fence_after();
-  if (warp == 2) tmem_dealloc<TMEM_COLS>(tmem_base);
+  if (warp == 2) { if (MMA2) tmem_dealloc_2sm<TMEM_COLS>(tmem_base); else tmem_dealloc<TMEM_COLS>(tmem_base); }
 }
 
 // ---- host side ----------------------------------------------------------------------------------------
@@ -437,12 +481,13 @@ int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int
   return B200Q_OK;
 }
 
-template <typename OutT, int EPI, bool W4, int NSTAGE, int CL>
+template <typename OutT, int EPI, bool W4, int NSTAGE, int PAIR>
 static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& to, const CUtensorMap& tr,
                           const GemmParams& p, cudaStream_t st) {
-  auto kern = gemm_i8_kernel<OutT, EPI, W4, NSTAGE, CL>;
+  constexpr int CL = PAIR ? 2 : 1;
+  auto kern = gemm_i8_kernel<OutT, EPI, W4, NSTAGE, PAIR>;
   static bool configured = false;    // cudaFuncSetAttribute once per instantiation, not per call
-  const int smem_bytes = GemmSmem<W4, NSTAGE>::total;
+  const int smem_bytes = GemmSmem<W4, NSTAGE, PAIR>::total;
   if (!configured) {
     B200Q_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes));
     configured = true;
@@ -454,7 +499,7 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
   if (grid > cap) grid = cap;
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3((unsigned)grid);
-  cfg.blockDim = dim3((unsigned)GemmSmem<W4, NSTAGE>::threads);
+  cfg.blockDim = dim3((unsigned)GemmSmem<W4, NSTAGE, PAIR>::threads);
   cfg.dynamicSmemBytes = (size_t)smem_bytes;
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
@@ -470,17 +515,23 @@ static int launch_gemm_cl(const CUtensorMap& ta, const CUtensorMap& tb, const CU
 // tb1: B tensor map with a full [256 x 128B] box (CL = 1); tb2: half box [128 x 128B] for the multicast path (CL = 2)
 struct GemmMaps { CUtensorMap a, b1, b2, out, res; };
 
-static int g_force_cluster = 0;     // 0 = auto, 1 = always CL 1, 2 = always CL 2 (debug/bench knob: b200q_gemm_set_cluster)
+// scheduling knob (b200q_gemm_set_cluster): 0 = auto, 1 = single-CTA tiles, 2 = 2-CTA clusters with multicast B,
+// 3 = 2-CTA clusters with tcgen05.mma.cta_group::2
+static int g_force_cluster = 0;
+// measured on B200 (tools/probe_gemm_modes.py): cta_group::2 pairs win for W8A8 (+3..15 %); the W4A8 converter warps
+// lose from the cross-CTA coupling, so W4A8 stays on single-CTA tiles
+static constexpr int kAutoPairW8 = 2, kAutoPairW4 = 0;
 
 template <typename OutT, int EPI, bool W4, int NSTAGE = 4>
 static int launch_gemm(const GemmMaps& m, const GemmParams& p, cudaStream_t st) {
   const int tiles_m = (p.M + BM - 1) / BM, tiles_n = (p.N + BN - 1) / BN;
   // pairs only pay off when there is more than one wave of tiles and at least two row blocks
-  bool pair = tiles_m >= 2 && tiles_m * tiles_n >= 2 * sm_count();
-  if (g_force_cluster == 1) pair = false;
-  if (g_force_cluster == 2) pair = tiles_m >= 2;
-  if (pair) return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 2>(m.a, m.b2, m.out, m.res, p, st);
-  return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 1>(m.a, m.b1, m.out, m.res, p, st);
+  int pair = (tiles_m >= 2 && tiles_m * tiles_n >= 2 * sm_count()) ? (W4 ? kAutoPairW4 : kAutoPairW8) : 0;
+  if (g_force_cluster == 1) pair = 0;
+  if (g_force_cluster >= 2) pair = tiles_m >= 2 ? g_force_cluster - 1 : 0;
+  if (pair == 2) return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 2>(m.a, m.b2, m.out, m.res, p, st);
+  if (pair == 1) return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 1>(m.a, m.b2, m.out, m.res, p, st);
+  return launch_gemm_cl<OutT, EPI, W4, NSTAGE, 0>(m.a, m.b1, m.out, m.res, p, st);
 }
 
 template <typename OutT, bool W4>
@@ -570,7 +621,7 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
 using namespace b200q;
 
 extern "C" int b200q_gemm_set_cluster(int mode) {
-  if (mode < 0 || mode > 2) return B200Q_ERR_BAD_ARG;
+  if (mode < 0 || mode > 3) return B200Q_ERR_BAD_ARG;
   g_force_cluster = mode;
   return B200Q_OK;
 }
