@@ -190,7 +190,39 @@ B200Q_API int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64
                        void* out, int64_t ldo, b200q_stream_t stream);
 
 /* ---- (c) quantized attention ------------------------------------------------------------
- * See DESIGN.md §attention; declared in later sections of this header as they land. */
+ * Replaces the reference's materialised fake-quant attention (examples/Wan2.1/models/quant_opensora.py:430-478:
+ * q/k/v DynamicQuantizers, `q*scale @ k^T`, fp32 softmax, attention-map quantizer, `attn @ v`), which builds
+ * S and P as [H, L, L] tensors and therefore cannot run at L = 32,760 / 75,600.
+ *
+ * b200q_quant_vt: V quantizer.  v [Lk, C] (fp32|bf16|fp16, row pitch ldv, C = heads*head_dim) -> vt int8 [C, Lk]
+ * (TRANSPOSED, row pitch ldvt: multiple of 16, >= Lk) and delta[C]: one symmetric scale per (head, channel) over all
+ * tokens = DynamicQuantizer on `v.permute(0,1,3,2).reshape(-1, N_token)` rows (quant_opensora.py:440-442;
+ * base_quantizer.py:110-129,151-157: delta = amax/n_levels, floor 1e-6, codes rne(x/delta) clamped).  absmax_ws [C] fp32
+ * is caller-owned scratch (the per-channel |v| maximum, computed by the calibration reduction kernel).
+ * The transposed layout makes a 128-key block of V a K-major B operand of the P.V product. */
+B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, int64_t ldv, int n_bits,
+                   float* absmax_ws, int8_t* vt, int64_t ldvt, float* delta, b200q_stream_t stream);
+
+/* b200q_attn_i8: fused int8 attention, head_dim = 128.
+ *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the
+ *   [L*H, 128] view); dq/dk: their fp32 scales, element (token, head) at dq[token*dq_tok_stride + head*dq_head_stride];
+ *   vtq int8 [H*128, Lk] (ldvt), dv fp32 [H*128]: from b200q_quant_vt.
+ *   S = qq.kq^T exact in int32 (tcgen05.mma.kind::i8); x = S*dq*dk*sm_scale; P~ = exp(x - rowmax x) quantized to unsigned
+ *   8 bit with step 1/255 (the [0, 2^b-1] grid of forward_with_quant_params, base_quantizer.py:197-199, one step per
+ *   query row); O = (P~q.vtq^T) exact in int32 * dv / (255 * sum_j P~).  out bf16 [Lq, H*128] (ldo).
+ *   Deviation from the reference's attention-map grouping ('row': one scale per KEY column over all queries,
+ *   quant_attn.py:168-174), which needs the whole [L, L] map first: see DESIGN.md; the parity path for that grouping is
+ *   wan/attention_q.py (small L).
+ *   Optional debug/parity outputs (NULL to skip): m_out, l_out fp32 [H, Lq] (row maximum in log2 units, row sum of P~);
+ *   p_out uint8 [H, Lq, ldp] (P~ codes; ldp multiple of 16 and >= ceil(Lk/128)*128); acc_out int32 [Lq, ldacc]
+ *   (raw P.V accumulators).  Lk <= 66,000 (int32 accumulator bound). */
+B200Q_API int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int64_t dq_tok_stride, int64_t dq_head_stride,
+                  const int8_t* kq, int64_t ldk, const float* dk, int64_t dk_tok_stride, int64_t dk_head_stride,
+                  const int8_t* vtq, int64_t ldvt, const float* dv,
+                  int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale,
+                  void* out, int out_dtype, int64_t ldo,
+                  float* m_out, float* l_out, uint8_t* p_out, int64_t ldp, int32_t* acc_out, int64_t ldacc,
+                  b200q_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -182,6 +182,33 @@ def quantized_attention_fake(q, k, v, qk_bits=8, qk_sym=True, v_bits=8, v_sym=Tr
     return attn @ v_dq, info
 
 
+def quantized_attention_rowstep(q, k, v, qk_bits=8, v_bits=8, p_bits=8, scale=None):
+    """Fused-kernel ("fast mode") attention semantics, restated with the reference's own quantizers:
+    Q,K per-(token,head) and V per-(head,channel) DynamicQuantizers exactly as quantized_attention_fake
+    (quant_opensora.py:430-442); S = (q_dq*scale) @ k_dq^T, fp32 softmax (:456-462); the attention map is quantized by
+    DynamicQuantizer.forward_with_quant_params (base_quantizer.py:164-206, unsigned [0, 2^b-1] grid) with
+    delta = the row maximum of P (one step per query row) instead of QuantizedAttentionMapOpenSORA's per-key-column
+    grouping.  Returns (out [B,H,Lq,hd], info) with info['p_codes'] = round(P / (rowmax/255)) in [0,255]."""
+    B, H, Lq, hd = q.shape
+    Lk = k.shape[2]
+    scale = hd ** -0.5 if scale is None else scale
+    qq, dq, zq = quant_rows(q.reshape(-1, hd), qk_bits, True, True)
+    kq, dk, zk = quant_rows(k.reshape(-1, hd), qk_bits, True, True)
+    vq, dv, zv = quant_rows(v.permute(0, 1, 3, 2).reshape(-1, Lk), v_bits, True, True)
+    q_dq = dequant_rows(qq, dq, zq).reshape(B, H, Lq, hd)
+    k_dq = dequant_rows(kq, dk, zk).reshape(B, H, Lk, hd)
+    v_dq = dequant_rows(vq, dv, zv).reshape(B, H, hd, Lk).permute(0, 1, 3, 2)
+    attn = ((q_dq * scale) @ k_dq.transpose(-2, -1)).float().softmax(dim=-1)
+    pmax = attn.max(dim=-1, keepdim=True)[0].expand_as(attn).clone()
+    p_dq = forward_with_quant_params(attn, pmax, p_bits)
+    nl = n_levels_of(p_bits, True) * 2 + 1
+    step = torch.where(pmax < 1.0e-6, torch.full_like(pmax, 1.0e-6), pmax) / nl
+    info = dict(qq=qq.reshape(B, H, Lq, hd), dq=dq.reshape(B, H, Lq), kq=kq.reshape(B, H, Lk, hd),
+                dk=dk.reshape(B, H, Lk), vq=vq.reshape(B, H, hd, Lk), dv=dv.reshape(B, H, hd), attn=attn,
+                p_codes=torch.clamp(torch.round(attn / step), 0, nl), p_dequant=p_dq)
+    return p_dq @ v_dq, info
+
+
 # --------------------------------------------------------------------------
 # one Wan DiT block (restatement; the reference block cannot run on CPU, SURVEY §8c)
 # --------------------------------------------------------------------------

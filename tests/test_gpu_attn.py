@@ -1,0 +1,144 @@
+"""-m gpu parity tests: fused int8 attention (b200q_attn_i8) and the V^T quantizer (b200q_quant_vt) through the C ABI.
+
+Bars: V codes / scales BIT-EXACT vs the oracle; int32 P.V accumulators BIT-EXACT (integer product of the kernel's own P~
+codes with the V codes); P~ codes within 1 LSB of the oracle (the kernel evaluates exp2 on the MUFU, the oracle uses
+torch.softmax: ties at the rounding boundary may differ), mismatch rate stated; outputs cosine >= 0.999 vs the oracle."""
+import os
+
+import pytest
+import torch
+
+import b200q
+from oracle import fakequant_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _cos(a, b):
+    a, b = a.double().flatten(), b.double().flatten()
+    return float((a @ b) / (a.norm() * b.norm() + 1e-30))
+
+
+def _heads(x, H):                      # [L, H*hd] -> [1, H, L, hd]
+    L, D = x.shape
+    return x.view(L, H, D // H).permute(1, 0, 2).unsqueeze(0).contiguous()
+
+
+def _run(q, k, v, H, dev, debug=True):
+    """q [Lq, D], k, v [Lk, D] fp32 CPU -> kernel outputs + the operands it consumed."""
+    Lq, D = q.shape
+    Lk = k.shape[0]
+    hd = D // H
+    qq, dq, _, _ = b200q.quant_rows(q.to(dev).reshape(Lq * H, hd), 8, True, True, want_rowsum=False)
+    kq, dk, _, _ = b200q.quant_rows(k.to(dev).reshape(Lk * H, hd), 8, True, True, want_rowsum=False)
+    vt, dv = b200q.quant_vt(v.to(dev), 8)
+    res = b200q.attn_i8(qq.view(Lq, D), dq.view(Lq, H), kq.view(Lk, D), dk.view(Lk, H), vt, dv, H, debug=debug)
+    torch.cuda.synchronize()
+    return res, dict(qq=qq.view(Lq, D), dq=dq.view(Lq, H), kq=kq.view(Lk, D), dk=dk.view(Lk, H), vt=vt, dv=dv)
+
+
+@pytest.mark.parametrize("Lk,C,dtype", [(300, 256, torch.float32), (257, 128, torch.bfloat16), (1024, 384, torch.bfloat16),
+                                        (77, 200, torch.float32), (130, 72, torch.float16)])
+def test_quant_vt_bit_exact(dev, Lk, C, dtype):
+    g = torch.Generator().manual_seed(Lk + C)
+    v = (torch.randn(Lk, C, generator=g) * (torch.rand(1, C, generator=g) * 3 + 0.01)).to(dtype)
+    v[:, 3] = 0                                     # zero channel -> delta floor 1e-6
+    vt, dv = b200q.quant_vt(v.to(dev), 8)
+    qo, do, _ = O.quant_rows(v.float().t().contiguous(), 8, True, True)
+    assert torch.equal(dv.cpu(), do.flatten())
+    assert torch.equal(vt.cpu().float(), qo)
+    # strided input (a column slice of a fused q|k|v projection)
+    big = torch.zeros(Lk, 3 * C, dtype=dtype)
+    big[:, 2 * C:] = v
+    if (2 * C * big.element_size()) % 16 == 0:
+        vt2, dv2 = b200q.quant_vt(big.to(dev)[:, 2 * C:], 8)
+        assert torch.equal(vt2.cpu(), vt.cpu()) and torch.equal(dv2.cpu(), dv.cpu())
+
+
+SHAPES = [(2, 300, 333), (1, 128, 128), (3, 700, 1100), (2, 1000, 512), (12, 3400, 260), (1, 5, 3)]
+
+
+@pytest.mark.parametrize("H,Lq,Lk", SHAPES)
+def test_attn_i8_parity(dev, H, Lq, Lk):
+    hd = 128
+    g = torch.Generator().manual_seed(H * 1000 + Lq + Lk)
+    q = torch.randn(Lq, H * hd, generator=g) * (torch.rand(Lq, 1, generator=g) * 2 + 0.2)
+    k = torch.randn(Lk, H * hd, generator=g) * (torch.rand(Lk, 1, generator=g) * 2 + 0.2)
+    v = torch.randn(Lk, H * hd, generator=g) * (torch.rand(1, H * hd, generator=g) * 2 + 0.1)
+    (out, dbg), ops = _run(q, k, v, H, dev)
+    qq, kq, vt = ops["qq"].cpu(), ops["kq"].cpu(), ops["vt"].cpu()
+    dq, dk, dv = ops["dq"].cpu(), ops["dk"].cpu(), ops["dv"].cpu()
+    p_codes, acc = dbg["p"].cpu(), dbg["acc"].cpu()
+
+    # operands are the oracle's (quantizer parity is tests/test_gpu_quant.py; re-checked here on the attention views)
+    ref_out, info = O.quantized_attention_rowstep(_heads(q, H), _heads(k, H), _heads(v, H))
+    assert torch.equal(_heads(qq.float(), H), info["qq"]) and torch.equal(_heads(kq.float(), H), info["kq"])
+    assert torch.equal(dq.t().unsqueeze(0), info["dq"]) and torch.equal(dk.t().unsqueeze(0), info["dk"])
+    assert torch.equal(vt.float().view(1, H, hd, Lk), info["vq"]) and torch.equal(dv.view(1, H, hd), info["dv"])
+
+    scale = hd ** -0.5
+    mism = 0
+    for h in range(H):
+        cols = slice(h * hd, (h + 1) * hd)
+        # (1) int32 accumulators of P.V: exact integer product of the kernel's own codes
+        want = p_codes[h].to(torch.int32) @ vt[cols].to(torch.int32).t()
+        assert torch.equal(acc[:, cols], want), f"head {h}: P.V accumulators not bit-exact"
+        # (2) P~ codes from the exact integer S in float64
+        S = O.int_accumulators(qq[:, cols].contiguous(), kq[:, cols].contiguous()).double()
+        x = S * dq[:, h].double()[:, None] * dk[:, h].double()[None, :] * scale
+        mrow = x.max(dim=1, keepdim=True)[0]
+        pt = torch.exp(x - mrow)
+        code64 = torch.round(pt * 255.0)
+        diff = (p_codes[h].double() - code64).abs()
+        assert diff.max() <= 1, f"head {h}: P code off by {diff.max()}"
+        mism += int((diff > 0).sum())
+        # and against the oracle's fp32 torch.softmax codes
+        assert (p_codes[h].float() - info["p_codes"][0, h]).abs().max() <= 1
+        # (3) row statistics
+        m_ref = (mrow.flatten() * 1.4426950408889634)
+        assert torch.allclose(dbg["m"][h].cpu().double(), m_ref, rtol=2e-5, atol=2e-4)
+        # fp32 exp2 arguments of magnitude ~50 carry ~1e-5 absolute error, and the folded int->float constant
+        # (-1.5*2^23*dk, one rounding) up to 0.75 LSB of S: relative error of P~ and l up to ~1e-4
+        assert torch.allclose(dbg["l"][h].cpu().double(), pt.sum(dim=1), rtol=5e-4)
+        # (4) the bf16 output is acc * dv / (255 * l)
+        o_ref = acc[:, cols].double() * dv[cols].double()[None, :] / (255.0 * dbg["l"][h].cpu().double()[:, None])
+        assert torch.allclose(out[:, cols].cpu().double(), o_ref, rtol=1e-2, atol=1e-6)
+    assert mism <= 0.01 * H * Lq * Lk, f"P code mismatch rate {mism / (H * Lq * Lk):.4f}"
+    ref2d = ref_out[0].permute(1, 0, 2).reshape(Lq, H * hd)
+    assert _cos(out.cpu(), ref2d) >= 0.9995
+    # fast mode vs unquantized attention on the same inputs
+    fp = torch.nn.functional.scaled_dot_product_attention(_heads(q, H), _heads(k, H), _heads(v, H))
+    assert _cos(out.cpu(), fp[0].permute(1, 0, 2).reshape(Lq, H * hd)) >= 0.999
+
+
+def test_attn_i8_golden(dev, golden_dir):
+    """tests/golden/quant_attention_rowstep.pt: outputs of the imported reference quantizers (oracle/gen_golden_attn.py)."""
+    rec = torch.load(os.path.join(golden_dir, "quant_attention_rowstep.pt"))
+    q, k, v = rec["q"], rec["k"], rec["v"]                    # [1, H, L, hd]
+    H, Lq, hd = q.shape[1], q.shape[2], q.shape[3]
+    Lk = k.shape[2]
+    flat = lambda x: x[0].permute(1, 0, 2).reshape(x.shape[2], H * hd).contiguous()
+    (out, dbg), ops = _run(flat(q), flat(k), flat(v), H, dev)
+    assert torch.equal(ops["dq"].cpu().t().reshape(-1), rec["q_delta"].flatten())
+    assert torch.equal(ops["dk"].cpu().t().reshape(-1), rec["k_delta"].flatten())
+    assert torch.equal(ops["dv"].cpu(), rec["v_delta"].flatten())
+    step = rec["attn"].max(dim=-1, keepdim=True)[0] / 255.0
+    ref_codes = torch.round(rec["attn_quant"] / step)[0]     # [H, Lq, Lk]
+    assert (dbg["p"].cpu().float() - ref_codes).abs().max() <= 1
+    assert _cos(out.cpu(), flat(rec["out"])) >= 0.9999
+
+
+def test_attn_i8_no_debug_matches_debug(dev):
+    H, Lq, Lk, hd = 2, 520, 700, 128
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(n, H * hd, generator=g) for n in (Lq, Lk, Lk))
+    (out_d, _), _ = _run(q, k, v, H, dev, debug=True)
+    out, _ = _run(q, k, v, H, dev, debug=False)
+    assert torch.equal(out.cpu(), out_d.cpu())
+
+
+def test_attn_i8_bad_args(dev):
+    qq = torch.zeros(8, 64, dtype=torch.int8, device=dev)
+    with pytest.raises(b200q.B200QError):                     # head_dim 64 is not supported
+        b200q.attn_i8(qq, torch.ones(8, 1, device=dev), qq, torch.ones(8, 1, device=dev),
+                      torch.zeros(64, 16, dtype=torch.int8, device=dev)[:, :8], torch.ones(64, device=dev), 1)

@@ -81,6 +81,20 @@ def test_quantized_attention(golden_dir):
     assert torch.equal(out, rec["out"])
 
 
+def test_quantized_attention_rowstep(golden_dir):
+    """Fused-kernel attention semantics (P quantized on the unsigned grid of forward_with_quant_params with one step per
+    query row): the oracle reproduces the imported reference quantizers bit-for-bit (oracle/gen_golden_attn.py)."""
+    rec = _load(golden_dir, "quant_attention_rowstep.pt")
+    out, info = O.quantized_attention_rowstep(rec["q"], rec["k"], rec["v"])
+    assert torch.equal(info["dq"].flatten(), rec["q_delta"].flatten())
+    assert torch.equal(info["dk"].flatten(), rec["k_delta"].flatten())
+    assert torch.equal(info["dv"].flatten(), rec["v_delta"].flatten())
+    assert torch.equal(info["attn"], rec["attn"])
+    assert torch.equal(info["p_dequant"], rec["attn_quant"])
+    assert torch.equal(out, rec["out"])
+    assert info["p_codes"].max() == 255 and info["p_codes"].min() == 0
+
+
 # ---- C restatement ---------------------------------------------------------------------------------------
 @pytest.fixture(scope="module")
 def clib():

@@ -57,6 +57,11 @@ _SIGNATURES = {
                                    c_void_p, c_int, c_int64, c_void_p]),
     "b200q_rmsnorm_rope": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                    c_int, c_void_p, c_int64, c_void_p]),
+    "b200q_quant_vt": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_int, c_void_p, c_void_p, c_int64, c_void_p,
+                               c_void_p]),
+    "b200q_attn_i8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
+                              c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_int,
+                              c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                     c_int64, c_int64, c_void_p]),
 }
@@ -312,6 +317,61 @@ def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0):
     rc = load().b200q_rmsnorm_rope(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(weight), float(eps), _ptr(cos),
                                    _ptr(sin), int(head_dim), _ptr(out), _ld(out), _stream())
     _check(rc, "b200q_rmsnorm_rope")
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+# (c) quantized attention
+# ---------------------------------------------------------------------------------------------
+def quant_vt(v, n_bits=8):
+    """v [Lk, C] -> (vt int8 [C, Lk] view of a 16-byte-pitched buffer, delta f32 [C]): one symmetric scale per
+    (head, channel) over all tokens (quant_opensora.py:440-442), codes stored transposed for the P.V product."""
+    _cuda(v, "quant_vt")
+    if v.dim() != 2 or v.stride(1) != 1:
+        raise B200QError("quant_vt: expected a row-major 2-D tensor")
+    Lk, C = v.shape
+    pitch = (Lk + 15) // 16 * 16
+    buf = torch.empty((C, pitch), dtype=torch.int8, device=v.device)
+    delta = torch.empty(C, dtype=torch.float32, device=v.device)
+    ws = torch.empty(C, dtype=torch.float32, device=v.device)
+    rc = load().b200q_quant_vt(_ptr(v), _DTYPE[v.dtype], Lk, C, _ld(v), int(n_bits), _ptr(ws), _ptr(buf), pitch,
+                               _ptr(delta), _stream())
+    _check(rc, "b200q_quant_vt")
+    return buf[:, :Lk], delta
+
+
+def attn_i8(qq, dq, kq, dk, vtq, dv, num_heads, sm_scale=None, out=None, debug=False):
+    """Fused int8 attention (include/b200q.h).  qq [Lq, H*128] int8, dq [Lq, H] f32 (any strides), kq/dk likewise,
+    vtq [H*128, Lk] int8 (row pitch multiple of 16), dv [H*128] f32 -> bf16 [Lq, H*128].
+    debug=True also returns dict(m, l, p, acc): row max (log2 units) / row sum [H, Lq], P~ codes uint8 [H, Lq, Lk],
+    raw int32 P.V accumulators [Lq, H*128]."""
+    for t, n in ((qq, "qq"), (dq, "dq"), (kq, "kq"), (dk, "dk"), (vtq, "vtq"), (dv, "dv")):
+        _cuda(t, n)
+    Lq, D = qq.shape
+    Lk = kq.shape[0]
+    H = int(num_heads)
+    hd = D // H
+    if dq.shape != (Lq, H) or dk.shape != (Lk, H) or vtq.shape != (D, Lk) or dv.numel() != D:
+        raise B200QError("attn_i8: shape mismatch")
+    sm_scale = hd ** -0.5 if sm_scale is None else float(sm_scale)
+    dev = qq.device
+    out = torch.empty((Lq, D), dtype=torch.bfloat16, device=dev) if out is None else out
+    m = l = pc = acc = None
+    ldp = 0
+    if debug:
+        m = torch.empty((H, Lq), dtype=torch.float32, device=dev)
+        l = torch.empty((H, Lq), dtype=torch.float32, device=dev)
+        ldp = (Lk + 127) // 128 * 128
+        pc = torch.zeros((H, Lq, ldp), dtype=torch.uint8, device=dev)
+        acc = torch.empty((Lq, D), dtype=torch.int32, device=dev)
+    dv = dv.contiguous()
+    rc = load().b200q_attn_i8(_ptr(qq), _ld(qq), _ptr(dq), dq.stride(0), dq.stride(1), _ptr(kq), _ld(kq), _ptr(dk),
+                              dk.stride(0), dk.stride(1), _ptr(vtq), _ld(vtq), _ptr(dv), Lq, Lk, H, hd, sm_scale,
+                              _ptr(out), BF16, _ld(out), _ptr(m), _ptr(l), _ptr(pc), ldp, _ptr(acc),
+                              _ld(acc) if acc is not None else 0, _stream())
+    _check(rc, "b200q_attn_i8")
+    if debug:
+        return out, dict(m=m, l=l, p=pc[:, :, :Lk], acc=acc)
     return out
 
 
