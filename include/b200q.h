@@ -189,6 +189,16 @@ B200Q_API int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64
                        const float* weight, float eps, const float* cos_t, const float* sin_t, int head_dim,
                        void* out, int64_t ldo, b200q_stream_t stream);
 
+/* Same, with the attention Q/K quantizer fused in: the rotated fp32 values are quantized per (token, head) — symmetric,
+ * delta = amax/n_levels with the 1e-6 floor, codes rne(y/delta) — exactly DynamicQuantizer on the [tokens*heads, head_dim]
+ * view (quant_opensora.py:430-435; base_quantizer.py:110-129,151-157).  q_out int8 [rows, cols] (ldq), dq_out fp32
+ * [rows, cols/head_dim].  head_dim must be 128 (pass head_dim = 128 even without RoPE tables, e.g. cross-attention q/k).
+ * `out` (bf16) may be NULL when only the codes are wanted. */
+B200Q_API int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                             const float* weight, float eps, const float* cos_t, const float* sin_t, int head_dim,
+                             void* out, int64_t ldo, int8_t* q_out, int64_t ldq, float* dq_out, int n_bits,
+                             b200q_stream_t stream);
+
 /* ---- (c) quantized attention ------------------------------------------------------------
  * Replaces the reference's materialised fake-quant attention (examples/Wan2.1/models/quant_opensora.py:430-478:
  * q/k/v DynamicQuantizers, `q*scale @ k^T`, fp32 softmax, attention-map quantizer, `attn @ v`), which builds
@@ -223,6 +233,10 @@ B200Q_API int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int6
                   void* out, int out_dtype, int64_t ldo,
                   float* m_out, float* l_out, uint8_t* p_out, int64_t ldp, int32_t* acc_out, int64_t ldacc,
                   b200q_stream_t stream);
+
+/* Scheduling knob of b200q_attn_i8 (debug / benchmarking; results identical): bit 0 = S accumulators pre-initialised
+ * with the int->fp32 conversion bias by tcgen05.st, bit 1 = pass 1 hands two key blocks per barrier round trip. */
+B200Q_API int b200q_attn_set_mode(int mode);
 
 #ifdef __cplusplus
 }

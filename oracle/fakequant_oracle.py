@@ -283,10 +283,18 @@ class WanBlockOracle:
             kw["w_bits"] = self.w_bits_by_layer[name]
         return quantized_linear_fake(x, w, b, **kw)
 
+    def cross_attention(self, q, k, v):
+        return self._attend(q, k, v)
+
     def attention(self, q, k, v):
+        return self._attend(q, k, v)
+
+    def _attend(self, q, k, v):
         # q,k,v [L,n,d] -> [1,n,L,d]
         q, k, v = (t.permute(1, 0, 2).unsqueeze(0) for t in (q, k, v))
-        if self.attn_quant is not None:
+        if self.attn_quant is not None and self.attn_quant.get("mode") == "rowstep":
+            o, _ = quantized_attention_rowstep(q, k, v, **{a: b for a, b in self.attn_quant.items() if a != "mode"})
+        elif self.attn_quant is not None:
             o, _ = quantized_attention_fake(q, k, v, **self.attn_quant)
         else:
             o = F.scaled_dot_product_attention(q, k, v)     # wan/modules/attention.py:171-178
@@ -311,8 +319,7 @@ class WanBlockOracle:
         q = rms_norm(self.lin("cross_attn.q", h), p["cross_attn.norm_q.weight"], self.eps).view(L, n, d)
         k = rms_norm(self.lin("cross_attn.k", context), p["cross_attn.norm_k.weight"], self.eps).view(T, n, d)
         v = self.lin("cross_attn.v", context).view(T, n, d)
-        qh, kh, vh = (t.permute(1, 0, 2).unsqueeze(0) for t in (q, k, v))
-        o = F.scaled_dot_product_attention(qh, kh, vh).squeeze(0).permute(1, 0, 2).flatten(1)
+        o = self.cross_attention(q, k, v)
         x = x + self.lin("cross_attn.o", o)
         # ffn  model.py:286-288, :359-362
         h = layer_norm(x, None, None, self.eps) * (1 + e[4]) + e[3]

@@ -121,3 +121,54 @@ def test_quantized_attention_parity_mode(dev, golden_dir):
     ref_out = rec["out"][0].permute(1, 0, 2).reshape(L, H * hd)
     c = float((out.cpu().double().flatten() @ ref_out.double().flatten()) / (out.cpu().double().norm() * ref_out.double().norm()))
     assert c >= 0.9999, c
+
+
+@pytest.mark.parametrize("dim,ffn,heads,grid", [(256, 512, 2, (2, 6, 8)), (384, 1024, 3, (3, 7, 13))])
+def test_block_int8_attention_matches_oracle(dev, dim, ffn, heads, grid):
+    """W8A8 linears + 8-bit Q.K^T / P.V attention (BASELINE configs[4] semantics) through the fused tcgen05 attention
+    kernel vs the oracle block whose attention is the row-step fake-quant attention (oracle pinned to the imported
+    reference quantizers, tests/golden/quant_attention_rowstep.pt)."""
+    cfg = M.WanConfig(dim=dim, ffn_dim=ffn, num_heads=heads, num_layers=1)
+    p = O.make_block_params(dim, ffn, seed=0)
+    L, T = grid[0] * grid[1] * grid[2], 40
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(L, dim, generator=g)
+    e = torch.randn(6, dim, generator=g) * 0.1
+    ctx = torch.randn(T, dim, generator=g)
+    ref = O.WanBlockOracle(p, dim, ffn, heads, attn_quant=dict(mode="rowstep")).forward(x.clone(), e, grid, ctx)
+    blk = M.WanBlockQ.from_fp_params(cfg, p, attn_quant=True)
+    cos, sin = M.rope_table(dim // heads, grid, dev)
+    n0 = b200q.launch_count
+    out = blk.forward(x.clone().to(dev), e.to(dev), ctx.to(dev), cos, sin).cpu()
+    assert b200q.launch_count - n0 >= 20
+    c = _cos(out, ref)
+    rel = float((out - ref).abs().max() / ref.abs().max())
+    assert c >= 0.999, c
+    assert rel <= 5e-2, rel
+
+
+@pytest.mark.parametrize("L,heads,grid", [(96, 2, (2, 6, 8)), (273, 3, (3, 7, 13))])
+def test_rmsnorm_rope_quant_kernel(dev, L, heads, grid):
+    """RMSNorm+RoPE with the fused per-(token, head) quantizer vs the oracle (float64 RoPE, then DynamicQuantizer on the
+    [L*H, 128] view): scales to 1e-5 relative, codes within one step (the kernel rotates in fp32), mismatch rate < 1 %;
+    the optional bf16 output is the plain rmsnorm_rope output."""
+    hd = 128
+    D = heads * hd
+    g = torch.Generator().manual_seed(L)
+    x = (torch.randn(L, 3 * D, generator=g) * 2).to(torch.bfloat16)
+    w = torch.rand(D, generator=g) + 0.5
+    cos, sin = M.rope_table(hd, grid, dev)
+    xs = x.to(dev)[:, D:2 * D]
+    q, dq, y = b200q.rmsnorm_rope_quant(xs, w.to(dev), 1e-6, cos, sin, hd, want_bf16=True)
+    ref = O.rope_apply(O.rms_norm(x[:, D:2 * D], w, 1e-6).view(L, heads, hd), grid, O.wan_freqs(hd))     # [L, H, hd] fp32
+    qo, do, _ = O.quant_rows(ref.reshape(L * heads, hd), 8, True, True)
+    assert torch.allclose(dq.cpu().flatten(), do.flatten(), rtol=1e-5)
+    diff = (q.cpu().float().view(L * heads, hd) - qo).abs()
+    assert diff.max() <= 1 and float((diff > 0).float().mean()) < 0.01
+    assert torch.equal(y.cpu(), b200q.rmsnorm_rope(xs, w.to(dev), 1e-6, cos, sin, hd).cpu())
+    # no RoPE (cross-attention q/k): codes of the RMSNorm output
+    q2, dq2, _ = b200q.rmsnorm_rope_quant(xs, w.to(dev), 1e-6, None, None, hd)
+    qo2, do2, _ = O.quant_rows(O.rms_norm(x[:, D:2 * D], w, 1e-6).reshape(L * heads, hd), 8, True, True)
+    assert torch.allclose(dq2.cpu().flatten(), do2.flatten(), rtol=1e-6)
+    d2 = (q2.cpu().float().view(L * heads, hd) - qo2).abs()
+    assert d2.max() <= 1 and float((d2 > 0).float().mean()) < 0.002

@@ -40,6 +40,12 @@ def main():
         vt, dv = b200q.quant_vt(v, 8)
         qq, kq, dq, dk = qq.view(Lq, D), kq.view(Lk, D), dq.view(Lq, H), dk.view(Lk, H)
         out = torch.empty(Lq, D, dtype=torch.bfloat16, device=dev)
+        modes = {}
+        for mode in (0, 1, 2, 3):
+            b200q.load().b200q_attn_set_mode(mode)
+            modes[mode] = timed(lambda: b200q.attn_i8(qq, dq, kq, dk, vt, dv, H, out=out))
+        best = min(modes, key=modes.get)
+        b200q.load().b200q_attn_set_mode(best)
         ms = timed(lambda: b200q.attn_i8(qq, dq, kq, dk, vt, dv, H, out=out))
         flops = 4.0 * Lq * Lk * D
         qh = q.view(Lq, H, 128).permute(1, 0, 2).unsqueeze(0)
@@ -54,7 +60,7 @@ def main():
         key = f"H{H}_Lq{Lq}_Lk{Lk}"
         res[key] = {"attn_i8_ms": ms, "attn_i8_tflops_equiv": flops / ms / 1e9, "int8_tops_3pass": 1.5 * flops / ms / 1e9,
                     "sdpa_bf16_ms": ms_lib, "sdpa_tflops": flops / ms_lib / 1e9, "cos_vs_bf16_sdpa": cos,
-                    "quant_vt_ms": ms_qv, "quant_rows_q_ms": ms_qq}
+                    "quant_vt_ms": ms_qv, "modes_ms": modes, "quant_rows_q_ms": ms_qq}
         print(key, json.dumps(res[key]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "probe_attn_i8.json"), "w"), indent=1)

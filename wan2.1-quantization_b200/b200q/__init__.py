@@ -62,6 +62,9 @@ _SIGNATURES = {
     "b200q_attn_i8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                               c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_int,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
+    "b200q_attn_set_mode": (c_int, [c_int]),
+    "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
+                                         c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                     c_int64, c_int64, c_void_p]),
 }
@@ -318,6 +321,23 @@ def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0):
                                    _ptr(sin), int(head_dim), _ptr(out), _ld(out), _stream())
     _check(rc, "b200q_rmsnorm_rope")
     return out
+
+
+def rmsnorm_rope_quant(x, weight, eps, cos=None, sin=None, head_dim=128, n_bits=8, want_bf16=False):
+    """RMSNorm (+ RoPE) with the attention Q/K quantizer fused in: returns (codes int8 [rows, cols], delta f32
+    [rows, cols/128], bf16 [rows, cols] | None).  Per-(token, head) symmetric scales (quant_opensora.py:430-435)."""
+    _cuda(x, "rmsnorm_rope_quant")
+    if x.dim() != 2 or x.stride(1) != 1:
+        raise B200QError("rmsnorm_rope_quant: expected a row-major 2-D tensor")
+    rows, cols = x.shape
+    q = torch.empty((rows, cols), dtype=torch.int8, device=x.device)
+    dq = torch.empty((rows, cols // head_dim), dtype=torch.float32, device=x.device)
+    out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    rc = load().b200q_rmsnorm_rope_quant(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(weight), float(eps), _ptr(cos),
+                                         _ptr(sin), int(head_dim), _ptr(out), _ld(out) if out is not None else 0,
+                                         _ptr(q), _ld(q), _ptr(dq), int(n_bits), _stream())
+    _check(rc, "b200q_rmsnorm_rope_quant")
+    return q, dq, out
 
 
 # ---------------------------------------------------------------------------------------------

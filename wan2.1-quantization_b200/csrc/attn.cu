@@ -45,8 +45,8 @@ constexpr int BQ = 128;            // queries per Q tile (one TMEM lane each)
 constexpr int BKEY = 128;          // keys per block
 constexpr int HD = 128;            // head dim == bytes per int8 row == one 128B swizzle row
 constexpr int TILE = 128 * 128;    // every operand tile is 16 KB
-constexpr int KS = 3, VS = 3, SCS = 4;
-constexpr int THREADS = 384;
+constexpr int KS = 4, VS = 3, SCS = 4;
+constexpr int THREADS = 352;             // 11 warps: the register file then allows 186 registers per thread
 constexpr uint32_t MAGIC_I = 0x4B400000u;    // bit pattern of 1.5*2^23: as_float(MAGIC_I + s) == 12582912 + s for |s| < 2^22
 constexpr float MAGIC_F = 12582912.0f;
 
@@ -69,6 +69,7 @@ struct Params {
   __nv_bfloat16* out; long long ldo;
   float scale_log2e;
   int n_items, n_qt;
+  int p1_two;                    // pass 1 hands two key blocks (256 S columns) to the warpgroup per barrier round trip
   float* m_out; float* l_out;
   uint8_t* p_out; long long ldp;
   int32_t* acc_out; long long ldacc;
@@ -85,6 +86,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
+// S accumulators are PRE-INITIALISED to MAGIC_I by the warpgroup that releases them (tcgen05.st) and every Q.K^T MMA
+// accumulates on top: the tensor core hands back MAGIC_I + S, whose bit pattern read as fp32 is 12582912 + S exactly, so
+// the int32 -> fp32 conversion costs no instruction (it is folded into the per-key FMA constant d = -12582912*dk).
+__device__ __forceinline__ void fill_magic(uint32_t taddr, int ncols) {
+  for (int c = 0; c < ncols; c += 16) tmem_st_32x16_splat(taddr + c, MAGIC_I);
+  tmem_st_wait();
+}
+
+template <bool PREMAGIC>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const Params p) {
@@ -102,9 +112,11 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   uint64_t* v_empty = v_full + VS;         // VS
   uint64_t* sc_full = v_empty + VS;        // SCS
   uint64_t* sc_empty = sc_full + SCS;      // SCS
-  uint64_t* s_full = sc_empty + SCS;       // [tile][buf] = 4
-  uint64_t* s_free = s_full + 4;           // 4
-  uint64_t* p_full = s_free + 4;           // [tile][pbuf] = 4
+  uint64_t* s_full = sc_empty + SCS;       // [tile]: S region written (pass 1: 256 columns, pass 2: 128)
+  uint64_t* s_free = s_full + 2;           // [tile]: S region drained and re-initialised
+  uint64_t* o_full = s_free + 2;           // [tile]: O accumulator complete
+  uint64_t* o_free = o_full + 2;           // [tile]: O columns drained and re-initialised
+  uint64_t* p_full = o_free + 2;           // [tile][pbuf] = 4
   uint64_t* p_free = p_full + 4;           // 4
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(p_free + 4);
 
@@ -116,10 +128,11 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < SCS; ++i) { mbar_init(&sc_full[i], 1); mbar_init(&sc_empty[i], 8); }
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < 2; ++i) {
       mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
-      mbar_init(&p_full[i], 4); mbar_init(&p_free[i], 1);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
     }
+    for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_free[i], 1); }
     fence_barrier_init();
   }
   if (warp == 8 && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
@@ -161,21 +174,18 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc_qk = idesc_i8(BQ, BKEY, true);
       constexpr uint32_t idesc_pv = idesc_i8(BQ, HD, false);
-      uint32_t use[2][2] = {{0, 0}, {0, 0}};        // how often S buffer [tile][buf] has been written so far
-      uint32_t pcnt[2] = {0, 0};                     // P tiles produced so far per Q tile
+      uint32_t useS[2] = {0, 0};                     // S-region uses so far per Q tile
+      uint32_t pcnt[2] = {0, 0};                     // P tiles consumed so far per Q tile
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
       const uint32_t q_addr = smem_u32(smem + Smem::q);
-      auto issue_qk = [&](int t, int b) {
-        mbar_wait(&s_free[t * 2 + b], (use[t][b] & 1) ^ 1);              // the warpgroup has drained the previous contents
-        tcgen05_fence_after();
+      // S[t][col .. col+127] += Q_t . K(stage)^T   (accumulates on the MAGIC_I pre-initialised columns)
+      auto qk = [&](int t, int col, int stage) {
         const uint64_t adesc = make_kmajor_sw128_desc(q_addr + t * TILE);
-        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + Smem::k + ks * TILE));
-        const uint32_t d = tmem_base + t * 256 + b * 128;
+        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(smem + Smem::k + stage * TILE));
+        const uint32_t d = tmem_base + t * 256 + col;
 #pragma unroll
         for (int k = 0; k < HD / 32; ++k)
-          mma_i8_ss(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_qk, k != 0 ? 1u : 0u);
-        mma_commit(&s_full[t * 2 + b]);
-        ++use[t][b];
+          mma_i8_ss(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_qk, (PREMAGIC || k != 0) ? 1u : 0u);
       };
       auto release_k = [&]() {
         mma_commit(&k_empty[ks]);
@@ -183,30 +193,49 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       };
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         mbar_wait(q_full, it & 1);
-        // ---- pass 1: S tiles only, double-buffered per Q tile ----
-        for (int j = 0; j < nb; ++j) {
+        // ---- pass 1: two key blocks (256 S columns) per hand-off ----
+        for (int j = 0; j < nb; j += (p.p1_two ? 2 : 1)) {
+          const bool two = j + 1 < nb && p.p1_two;
+          const int ks2 = (ks + 1 == KS) ? 0 : ks + 1;
           mbar_wait(&k_full[ks], kph);
-          issue_qk(0, j & 1);
-          issue_qk(1, j & 1);
+          if (two) mbar_wait(&k_full[ks2], (ks + 1 == KS) ? (kph ^ 1) : kph);
+          for (int t = 0; t < 2; ++t) {
+            mbar_wait(&s_free[t], useS[t] & 1);
+            if (j == 0) mbar_wait(&o_free[t], it & 1);                   // the O columns double as S columns in pass 1
+            tcgen05_fence_after();
+            qk(t, 0, ks);
+            if (two) qk(t, 128, ks2);
+            mma_commit(&s_full[t]);
+            ++useS[t];
+          }
           release_k();
+          if (two) release_k();
         }
         // ---- pass 2 ----
         mbar_wait(&k_full[ks], kph);
-        issue_qk(0, 0);
-        issue_qk(1, 0);
+        for (int t = 0; t < 2; ++t) {
+          mbar_wait(&s_free[t], useS[t] & 1);
+          tcgen05_fence_after();
+          qk(t, 0, ks);
+          mma_commit(&s_full[t]);
+          ++useS[t];
+        }
         release_k();
         if (nb == 1) mma_commit(q_empty);
         for (int j = 0; j < nb; ++j) {
           const bool more = j + 1 < nb;
           if (more) mbar_wait(&k_full[ks], kph);
           for (int t = 0; t < 2; ++t) {
-            if (more) issue_qk(t, 0);                                    // S(j+1) as soon as S(j) has been read
+            if (more) {                                                  // S(j+1) as soon as S(j) has been read
+              mbar_wait(&s_free[t], useS[t] & 1);
+              tcgen05_fence_after();
+              qk(t, 0, ks);
+              mma_commit(&s_full[t]);
+              ++useS[t];
+            }
             if (more && t == 1) {
               release_k();
               if (j + 2 == nb) mma_commit(q_empty);                      // last read of the Q tiles
-            }
-            if (j == 0) {                                                // O columns: last used as pass-1 S buffer / previous item's O
-              mbar_wait(&s_free[t * 2 + 1], (use[t][1] & 1) ^ 1);
             }
             if (t == 0) mbar_wait(&v_full[vs], vph);
             const int pb = pcnt[t] & 1;
@@ -220,7 +249,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
               mma_i8_ss(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc_pv, (j | k) != 0 ? 1u : 0u);
             mma_commit(&p_free[t * 2 + pb]);
             ++pcnt[t];
-            if (!more) { mma_commit(&s_full[t * 2 + 1]); ++use[t][1]; }   // O complete
+            if (!more) mma_commit(&o_full[t]);                           // O complete
           }
           mma_commit(&v_empty[vs]);
           if (++vs == VS) { vs = 0; vph ^= 1; }
@@ -257,10 +286,19 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     const int t = warp >> 2, quarter = warp & 3;
     const int r = quarter * 32 + lane;                                   // row inside the Q tile == TMEM lane
     const uint32_t t_lane = tmem_base + t * 256 + ((uint32_t)(quarter * 32) << 16);
-    uint32_t use0 = 0, use1 = 0, pcnt = 0;
+    uint32_t useS = 0, pcnt = 0, itn = 0;
     int scs = 0; uint32_t scph = 0;
+    constexpr uint32_t MG = PREMAGIC ? 0u : MAGIC_I;                      // int -> fp32 bias added here unless pre-initialised
     const uint64_t magic2 = pack_f32x2(MAGIC_F, MAGIC_F), c255 = pack_f32x2(255.f, 255.f);
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+    auto release = [&](uint64_t* bar) {                                  // TMEM reads/writes of this warp done -> MMA issuer
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar);
+    };
+    if (PREMAGIC) fill_magic(t_lane, 256);
+    release(&s_free[t]);
+    release(&o_free[t]);
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
       const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
       const int row = q0 + r;
       const bool row_ok = row < p.Lq;
@@ -268,37 +306,34 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
 
       // ---- pass 1: m = max_j S[i,j]*dk[j] ----
       float m = -INFINITY;
-      for (int j = 0; j < nb; ++j) {
-        const int b = j & 1;
-        const uint32_t u = b ? use1 : use0;
-        mbar_wait(&sc_full[scs], scph);
-        mbar_wait(&s_full[t * 2 + b], u & 1);
+      for (int j = 0; j < nb; j += (p.p1_two ? 2 : 1)) {
+        const int nblk = (j + 1 < nb && p.p1_two) ? 2 : 1;
+        mbar_wait(&s_full[t], useS & 1);
         tcgen05_fence_after();
-        const float4* s4 = reinterpret_cast<const float4*>(smem + Smem::sc + scs * 1024);
+        for (int hb = 0; hb < nblk; ++hb) {
+          mbar_wait(&sc_full[scs], scph);
+          const float4* s4 = reinterpret_cast<const float4*>(smem + Smem::sc + scs * 1024);
 #pragma unroll
-        for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_lane + b * 128 + ch * 32, v);
-          tmem_ld_wait();
-          if (ch == 3) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[t * 2 + b]);
-          }
+          for (int ch = 0; ch < 4; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(t_lane + hb * 128 + ch * 32, v);
+            tmem_ld_wait();
 #pragma unroll
-          for (int e = 0; e < 32; e += 2) {
-            const float4 cd = s4[(ch * 32 + e) >> 1];
-            const uint64_t t2 = fma_f32x2(pack_u32x2(v[e] + MAGIC_I, v[e + 1] + MAGIC_I), pack_f32x2(cd.x, cd.y),
-                                          pack_f32x2(cd.z, cd.w));
-            float t0, t1;
-            unpack_f32x2(t2, t0, t1);
-            m = fmaxf(m, fmaxf(t0, t1));
+            for (int e = 0; e < 32; e += 2) {
+              const float4 cd = s4[(ch * 32 + e) >> 1];
+              const uint64_t t2 = fma_f32x2(pack_u32x2(v[e] + MG, v[e + 1] + MG), pack_f32x2(cd.x, cd.y), pack_f32x2(cd.z, cd.w));
+              float t0, t1;
+              unpack_f32x2(t2, t0, t1);
+              m = fmaxf(m, fmaxf(t0, t1));
+            }
           }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&sc_empty[scs]);
+          if (++scs == SCS) { scs = 0; scph ^= 1; }
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sc_empty[scs]);
-        if (++scs == SCS) { scs = 0; scph ^= 1; }
-        if (b) ++use1; else ++use0;
+        if (PREMAGIC) fill_magic(t_lane, nblk * 128);
+        release(&s_free[t]);
+        ++useS;
       }
 
       // ---- pass 2: P~ = exp2((S*dk - m)*a) -> u8 codes -> smem ; l = sum P~ ----
@@ -310,7 +345,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         const int pb = pcnt & 1;
         mbar_wait(&sc_full[scs], scph);
         mbar_wait(&p_free[t * 2 + pb], ((pcnt >> 1) & 1) ^ 1);           // P.V of two blocks ago has consumed this buffer
-        mbar_wait(&s_full[t * 2], use0 & 1);
+        mbar_wait(&s_full[t], useS & 1);
         tcgen05_fence_after();
         const float4* s4 = reinterpret_cast<const float4*>(smem + Smem::sc + scs * 1024);
         uint8_t* prow = smem + Smem::p + (t * 2 + pb) * TILE + r * 128;
@@ -319,19 +354,16 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           uint32_t v[32];
           tmem_ld_32x32(t_lane + ch * 32, v);
           tmem_ld_wait();
-          if (ch == 3) {
-            tcgen05_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&s_free[t * 2]);
+          if (ch == 3) {                                                 // S(j) is in registers: hand the columns back
+            if (PREMAGIC) fill_magic(t_lane, 128);
+            release(&s_free[t]);
           }
           uint32_t w[8];
 #pragma unroll
           for (int e = 0; e < 32; e += 4) {
             const float4 cd0 = s4[(ch * 32 + e) >> 1], cd1 = s4[((ch * 32 + e) >> 1) + 1];
-            uint64_t t01 = fma_f32x2(pack_u32x2(v[e] + MAGIC_I, v[e + 1] + MAGIC_I), pack_f32x2(cd0.x, cd0.y),
-                                     pack_f32x2(cd0.z, cd0.w));
-            uint64_t t23 = fma_f32x2(pack_u32x2(v[e + 2] + MAGIC_I, v[e + 3] + MAGIC_I), pack_f32x2(cd1.x, cd1.y),
-                                     pack_f32x2(cd1.z, cd1.w));
+            uint64_t t01 = fma_f32x2(pack_u32x2(v[e] + MG, v[e + 1] + MG), pack_f32x2(cd0.x, cd0.y), pack_f32x2(cd0.z, cd0.w));
+            uint64_t t23 = fma_f32x2(pack_u32x2(v[e + 2] + MG, v[e + 3] + MG), pack_f32x2(cd1.x, cd1.y), pack_f32x2(cd1.z, cd1.w));
             t01 = fma_f32x2(t01, a2, nma2);
             t23 = fma_f32x2(t23, a2, nma2);
             float x0, x1, x2, x3;
@@ -361,7 +393,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           mbar_arrive(&sc_empty[scs]);
         }
         if (++scs == SCS) { scs = 0; scph ^= 1; }
-        ++use0; ++pcnt;
+        ++useS; ++pcnt;
       }
 
       // ---- read-out: O = acc * dv[c] / (255 * l) ----
@@ -369,7 +401,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       unpack_f32x2(sum2, s0, s1);
       const float l = s0 + s1;
       const float inv = 1.0f / (255.0f * l);
-      mbar_wait(&s_full[t * 2 + 1], use1 & 1);
+      mbar_wait(&o_full[t], itn & 1);
       tcgen05_fence_after();
       if (row_ok && p.m_out != nullptr) p.m_out[(long long)h * p.Lq + row] = m * a;
       if (row_ok && p.l_out != nullptr) p.l_out[(long long)h * p.Lq + row] = l;
@@ -380,9 +412,8 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         tmem_ld_32x32(t_lane + 128 + ch * 32, v);
         tmem_ld_wait();
         if (ch == 3) {
-          tcgen05_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&s_free[t * 2 + 1]);
+          if (PREMAGIC) fill_magic(t_lane + 128, 128);
+          release(&o_free[t]);
         }
         if (row_ok) {
           if (p.acc_out != nullptr) {
@@ -405,7 +436,6 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           }
         }
       }
-      ++use1;
     }
   }
 
@@ -517,6 +547,15 @@ extern "C" int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C,
   return B200Q_OK;
 }
 
+// scheduling knob (b200q_attn_set_mode): bit 0 = S accumulators pre-initialised with the int->fp32 bias (tcgen05.st),
+// bit 1 = pass 1 hands two key blocks per barrier round trip.  Results are identical.
+static int g_attn_mode = 2;   // measured on B200 (tools/probe_attn_i8.py, H=12 L=32760): mode 0 7.99 ms, 1 8.77, 2 7.57, 3 8.55
+extern "C" int b200q_attn_set_mode(int mode) {
+  if (mode < 0 || mode > 3) return B200Q_ERR_BAD_ARG;
+  g_attn_mode = mode;
+  return B200Q_OK;
+}
+
 extern "C" int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int64_t dq_tok_stride, int64_t dq_head_stride,
                              const int8_t* kq, int64_t ldk, const float* dk, int64_t dk_tok_stride, int64_t dk_head_stride,
                              const int8_t* vtq, int64_t ldvt, const float* dv, int64_t Lq, int64_t Lk, int num_heads,
@@ -562,11 +601,14 @@ extern "C" int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int
 
   static bool configured = false;
   if (!configured) {
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     configured = true;
   }
+  p.p1_two = (g_attn_mode & 2) ? 1 : 0;
   int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  attn_i8_kernel<<<grid, THREADS, Smem::total, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  if (g_attn_mode & 1) attn_i8_kernel<true><<<grid, THREADS, Smem::total, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  else attn_i8_kernel<false><<<grid, THREADS, Smem::total, (cudaStream_t)stream>>>(tq, tk, tv, p);
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }

@@ -245,6 +245,12 @@ struct RopeArgs {
   int head_dim;
   void* out;
   int64_t ldo;
+  // optional fused per-(token, head) symmetric quantizer of the rotated fp32 values (attention Q/K operands,
+  // quant_opensora.py:430-435 = DynamicQuantizer on [tokens*heads, head_dim] rows): codes [rows, cols], scales [rows, heads]
+  int8_t* q_out;
+  int64_t ldq;
+  float* dq_out;
+  float n_levels;
 };
 
 template <typename T, int V, int THREADS>
@@ -313,10 +319,34 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
         y[2 * i + 1] = re * sv[i] + im * cv[i];
       }
     }
-    __nv_bfloat162 o[4];
+    if (a.out != nullptr) {
+      __nv_bfloat162 o[4];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
-    stg_stream16(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + c0, *reinterpret_cast<uint4*>(o));
+      for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
+      stg_stream16(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + c0, *reinterpret_cast<uint4*>(o));
+    }
+    if (a.q_out != nullptr) {
+      // a head (head_dim == 128 == 16 vectors) is held by 16 consecutive lanes: |y| max by 4 shuffles.  Every lane of
+      // the group is live (cols is a multiple of head_dim), so the partial-warp shuffles below are well defined.
+      float am = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i) am = fmaxf(am, fabsf(y[i]));
+      const unsigned grp = 0xffffu << (lane & 16);
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(grp, am, o));
+      float d = am / a.n_levels;                              // base_quantizer.py:119
+      if (d < 1e-6f) d = 1e-6f;                               // :122-128
+      const float rcp = 1.0f / d;
+      uint32_t w[2] = {0u, 0u};
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        int qv = rne_to_int(div_rn_hoisted(y[i], d, rcp));
+        qv = max(-(int)a.n_levels - 1, min((int)a.n_levels, qv));
+        w[i >> 2] |= ((uint32_t)qv & 0xffu) << (8 * (i & 3));
+      }
+      stg_stream8(a.q_out + row * a.ldq + c0, make_uint2(w[0], w[1]));
+      if ((lane & 15) == 0) a.dq_out[row * (a.cols / a.head_dim) + c0 / a.head_dim] = d;
+    }
   }
 }
 
@@ -470,13 +500,30 @@ extern "C" int b200q_gate_residual(const void* y, int y_dtype, int64_t ldy, cons
 extern "C" int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, const float* weight,
                                   float eps, const float* cos_t, const float* sin_t, int head_dim, void* out, int64_t ldo,
                                   b200q_stream_t stream) {
+  B200Q_REQUIRE(out != nullptr || rows == 0 || cols == 0, B200Q_ERR_BAD_ARG, "rmsnorm_rope: null pointer");
+  return b200q_rmsnorm_rope_quant(x, x_dtype, rows, cols, ldx, weight, eps, cos_t, sin_t, head_dim, out, ldo, nullptr, 0,
+                                  nullptr, 8, stream);
+}
+
+extern "C" int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                                        const float* weight, float eps, const float* cos_t, const float* sin_t,
+                                        int head_dim, void* out, int64_t ldo, int8_t* q_out, int64_t ldq, float* dq_out,
+                                        int n_bits, b200q_stream_t stream) {
   clear_error();
   B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "rmsnorm_rope: negative shape");
   if (rows == 0 || cols == 0) return B200Q_OK;
-  B200Q_REQUIRE(x && weight && out, B200Q_ERR_BAD_ARG, "rmsnorm_rope: null pointer");
+  B200Q_REQUIRE(x && weight && (out || q_out), B200Q_ERR_BAD_ARG, "rmsnorm_rope: null pointer");
+  if (q_out) {
+    B200Q_REQUIRE(dq_out != nullptr, B200Q_ERR_BAD_ARG, "rmsnorm_rope_quant: dq_out required with q_out");
+    B200Q_REQUIRE(head_dim == 128 && cols % 128 == 0, B200Q_ERR_UNSUPPORTED,
+                  "rmsnorm_rope_quant: the fused per-(token, head) quantizer needs head_dim == 128");
+    B200Q_REQUIRE(ldq >= cols && ldq % 8 == 0 && aligned(q_out, 8), B200Q_ERR_BAD_ARG, "rmsnorm_rope_quant: bad q_out layout");
+    B200Q_REQUIRE(n_bits >= 2 && n_bits <= 8, B200Q_ERR_BAD_ARG, "rmsnorm_rope_quant: n_bits out of [2,8]");
+  }
+  if (out == nullptr) ldo = cols;
   B200Q_REQUIRE(x_dtype == B200Q_BF16 || x_dtype == B200Q_F16, B200Q_ERR_BAD_ARG, "rmsnorm_rope: x must be bf16 or fp16");
   B200Q_REQUIRE(cols % 8 == 0 && ldx % 8 == 0 && ldo % 8 == 0 && ldx >= cols && ldo >= cols && aligned(x, 16) &&
-                    aligned(out, 16) && aligned(weight, 16),
+                    (out == nullptr || aligned(out, 16)) && aligned(weight, 16),
                 B200Q_ERR_UNSUPPORTED, "rmsnorm_rope: cols/ldx/ldo must be multiples of 8 and pointers 16-byte aligned");
   B200Q_REQUIRE((cos_t == nullptr) == (sin_t == nullptr), B200Q_ERR_BAD_ARG, "rmsnorm_rope: cos and sin go together");
   if (cos_t) {
@@ -486,6 +533,7 @@ extern "C" int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int6
   RopeArgs a{};
   a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.weight = weight; a.eps = eps; a.cos_t = cos_t; a.sin_t = sin_t;
   a.head_dim = head_dim > 0 ? head_dim : (int)cols; a.out = out; a.ldo = ldo;
+  a.q_out = q_out; a.ldq = ldq; a.dq_out = dq_out; a.n_levels = (float)((1 << (n_bits - 1)) - 1);
   if (x_dtype == B200Q_BF16) return launch_rope<__nv_bfloat16>(a, (cudaStream_t)stream);
   return launch_rope<__half>(a, (cudaStream_t)stream);
 }

@@ -195,6 +195,13 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t* v) {
       : "r"(taddr)
       : "memory");
 }
+// 32 lanes x 16 consecutive 32-bit columns, every element = val (accumulator pre-initialisation)
+__device__ __forceinline__ void tmem_st_32x16_splat(uint32_t taddr, uint32_t val) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1,%1};" ::"r"(taddr), "r"(val)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // K-major operand tile [rows][128 B] written by TMA with SWIZZLE_128B: 8-row groups of 1024 B.

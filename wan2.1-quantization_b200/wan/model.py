@@ -159,6 +159,20 @@ def rmsnorm_rope(x, weight, eps, cos=None, sin=None, num_heads=1):
     return b200q.rmsnorm_rope(x, weight, eps, cos, sin, x.shape[1] // num_heads)
 
 
+def attention_i8(q, k, v, num_heads):
+    """Fused int8 attention on bf16 q,k,v [L, H*128] (fast mode, include/b200q.h b200q_attn_i8): Q,K per-(token,head)
+    and V per-(head,channel) quantizers of quant_opensora.py:430-442, then the tcgen05 kernel.  Used after the Ulysses
+    exchange (the V scale spans all tokens of a head); the single-GPU path fuses the Q/K quantizer into
+    rmsnorm_rope instead."""
+    Lq, D = q.shape
+    Lk = k.shape[0]
+    hd = D // num_heads
+    qq, dq, _, _ = b200q.quant_rows(q.reshape(Lq * num_heads, hd), 8, True, True, want_rowsum=False)
+    kq, dk, _, _ = b200q.quant_rows(k.reshape(Lk * num_heads, hd), 8, True, True, want_rowsum=False)
+    vt, dv = b200q.quant_vt(v, 8)
+    return b200q.attn_i8(qq.view(Lq, D), dq.view(Lq, num_heads), kq.view(Lk, D), dk.view(Lk, num_heads), vt, dv, num_heads)
+
+
 def sdpa(q, k, v, num_heads):
     """q [Lq, H*hd], k,v [Lk, H*hd] bf16 -> [Lq, H*hd] bf16 via the library flash attention
     (the reference calls flash-attn, wan/modules/attention.py:94-127)."""
@@ -177,8 +191,10 @@ def sdpa(q, k, v, num_heads):
 class WanBlockQ:
     """Integer runtime of WanAttentionBlock.forward (wan/modules/model.py:293-370)."""
 
-    def __init__(self, cfg: WanConfig, w: dict, a_bits=8):
-        self.cfg, self.a_bits = cfg, a_bits
+    def __init__(self, cfg: WanConfig, w: dict, a_bits=8, attn_quant=False):
+        """attn_quant: 8-bit Q.K^T / P.V attention (quant_config `attn.qk`, `attn.v`, `attn.attn_map`, SURVEY §8 a-8 /
+        BASELINE configs[4]) through the fused int8 kernel instead of the library bf16 flash attention."""
+        self.cfg, self.a_bits, self.attn_quant = cfg, a_bits, attn_quant
         self.w_qkv = w["self_attn.qkv"]
         self.w_o = w["self_attn.o"]
         self.w_cq, self.w_ckv, self.w_co = w["cross_attn.q"], w["cross_attn.kv"], w["cross_attn.o"]
@@ -190,7 +206,7 @@ class WanBlockQ:
         self.attention_fn = None          # set by the sequence-parallel wrapper / int8 attention
 
     @staticmethod
-    def from_fp_params(cfg: WanConfig, p: dict, w_bits=8, w_sym=False, w_bits_by_layer=None):
+    def from_fp_params(cfg: WanConfig, p: dict, w_bits=8, w_sym=False, w_bits_by_layer=None, attn_quant=False):
         """p: fp32 tensors keyed like oracle.fakequant_oracle.make_block_params (same names as the module tree)."""
         w_bits_by_layer = w_bits_by_layer or {}
 
@@ -209,10 +225,10 @@ class WanBlockQ:
                   "cross_attn.norm_k.weight", "norm3.weight", "norm3.bias", "modulation"):
             if k in p:
                 w[k] = p[k].detach().float().cuda().contiguous()
-        return WanBlockQ(cfg, w)
+        return WanBlockQ(cfg, w, attn_quant=attn_quant)
 
     @staticmethod
-    def random(cfg: WanConfig, generator=None, w_bits=8, ffn_bits=None):
+    def random(cfg: WanConfig, generator=None, w_bits=8, ffn_bits=None, attn_quant=False):
         D, Fd = cfg.dim, cfg.ffn_dim
         fb = ffn_bits or w_bits
         dev = "cuda"
@@ -229,9 +245,12 @@ class WanBlockQ:
         }
         for k in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight", "cross_attn.norm_k.weight"):
             w[k] = torch.ones(D, device=dev)
-        return WanBlockQ(cfg, w)
+        return WanBlockQ(cfg, w, attn_quant=attn_quant)
 
     # ---- forward ------------------------------------------------------------------------------------------
+    def _default_attention(self, q, k, v):
+        return sdpa(q, k, v, self.cfg.num_heads)
+
     def context_kv(self, context):
         """cross-attention K,V of the (rank-replicated) text context [T, D] — token-local, once per block."""
         cfg = self.cfg
@@ -240,27 +259,48 @@ class WanBlockQ:
         k = rmsnorm_rope(kv[:, :cfg.dim], self.cnorm_k, cfg.eps)
         return k, kv[:, cfg.dim:]
 
+    def context_kv_i8(self, context):
+        """int8 operands of the cross-attention keys/values: (kq, dk, vt, dv)."""
+        cfg = self.cfg
+        qc, dc, _, rc = b200q.quant_rows(context, self.a_bits, True, True)
+        kv = qlinear(qc, dc, rc, self.w_ckv)
+        kq, dk, _ = b200q.rmsnorm_rope_quant(kv[:, :cfg.dim], self.cnorm_k, cfg.eps, None, None, cfg.head_dim)
+        vt, dv = b200q.quant_vt(kv[:, cfg.dim:], 8)
+        return kq, dk, vt, dv
+
     def forward(self, x, e0, context, cos, sin, attention=None):
         """x [L, D] fp32 (updated in place and returned), e0 [6, D] fp32, context [T, D] fp32/bf16."""
         cfg = self.cfg
         D, H = cfg.dim, cfg.num_heads
         e = self.modulation + e0                                                # model.py:322-324 (fp32)
-        attention = attention or self.attention_fn or (lambda q, k, v: sdpa(q, k, v, H))
+        local_attention = attention is None and self.attention_fn is None       # no sequence-parallel exchange in the way
+        attention = attention or self.attention_fn or self._default_attention
 
         # ---- self attention (model.py:327-337 with xdit_context_parallel.py:163-165 semantics) ----
         qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, shift=e[0], scale=e[1], n_bits=self.a_bits)
         qkv = qlinear(qa, da, rs, self.w_qkv)                                   # [L, 3D] bf16
-        q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H)
-        k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H)
-        a = attention(q, k, qkv[:, 2 * D:])
+        if self.attn_quant and local_attention:
+            # token-local int8 path: Q/K codes straight out of the RMSNorm+RoPE kernel, V^T codes, fused attention
+            qq, dq, _ = b200q.rmsnorm_rope_quant(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, cfg.head_dim)
+            kq, dk, _ = b200q.rmsnorm_rope_quant(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, cfg.head_dim)
+            vt, dv = b200q.quant_vt(qkv[:, 2 * D:], 8)
+            a = b200q.attn_i8(qq, dq, kq, dk, vt, dv, H)
+        else:
+            q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H)
+            k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H)
+            a = attention(q, k, qkv[:, 2 * D:])
         qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
         qlinear(qa, da, rs, self.w_o, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[2])
 
         # ---- cross attention (model.py:180-200, 351-353) ----
         qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, ln_w=self.norm3_w, ln_b=self.norm3_b, n_bits=self.a_bits)
-        q = rmsnorm_rope(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps)
-        ck, cv = self.context_kv(context)
-        a = sdpa(q, ck, cv, H)
+        if self.attn_quant:
+            qq, dq, _ = b200q.rmsnorm_rope_quant(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps, None, None, cfg.head_dim)
+            a = b200q.attn_i8(qq, dq, *self.context_kv_i8(context), H)
+        else:
+            q = rmsnorm_rope(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps)
+            ck, cv = self.context_kv(context)
+            a = sdpa(q, ck, cv, H)
         qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
         qlinear(qa, da, rs, self.w_co, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=None)
 
@@ -295,13 +335,15 @@ class WanDiTQ:
         self.cfg, self.blocks, self.fp, self.sp = cfg, blocks, fp, sp
 
     @staticmethod
-    def random(cfg: WanConfig, seed=0, w_bits=8, ffn_bits=None, sp=None, num_layers=None):
+    def random(cfg: WanConfig, seed=0, w_bits=8, ffn_bits=None, sp=None, num_layers=None, attn_quant=False):
         """Random-init weights of the named architecture (no checkpoints offline): blocks as codes+scales on device,
         FP parts with WanModel.init_weights statistics (model.py:658-680)."""
         g = torch.Generator(device="cuda").manual_seed(seed)
         D = cfg.dim
         n = num_layers or cfg.num_layers
-        blocks = [WanBlockQ.random(cfg, g, w_bits, ffn_bits) for _ in range(n)]
+        blocks = [WanBlockQ.random(cfg, g, w_bits, ffn_bits, attn_quant) for _ in range(n)]
+        if attn_quant and sp is not None:
+            sp.attention_core = attention_i8
 
         def lin(o, i, std=None):
             a = math.sqrt(6.0 / (i + o))
