@@ -43,6 +43,14 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--layers", type=int, default=None, help="debug only: fewer blocks (result is then marked invalid)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--model", default="1.3B", choices=["1.3B", "14B"],
+                    help="1.3B @ 832x480x81 = BASELINE configs[1] (default, the headline); 14B @ 1280x720x81 = configs[3]")
+    ap.add_argument("--attn", default="bf16", choices=["bf16", "int8"],
+                    help="attention core: library bf16 flash attention (configs[1]) or the fused int8 Q.K^T/P.V kernel (configs[4])")
+    ap.add_argument("--ffn-bits", type=int, default=8, choices=[4, 8], help="4 = W4A8 FFN weights (configs[4])")
+    ap.add_argument("--no-variants", action="store_true", help="skip the extra int8-attention timing at N=1")
+    ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: hard-exit after this wall-clock time")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 
 
@@ -221,9 +229,14 @@ def run_b200(args):
     if rc != 0:
         raise SystemExit("libb200q: " + b200q.load().b200q_last_error().decode())
 
-    cfg = M.WAN_1_3B
+    global LATENT_SHAPE
+    cfg = M.WAN_1_3B if args.model == "1.3B" else M.WAN_14B
+    if args.model == "14B":
+        LATENT_SHAPE = (16, 21, 90, 160)                        # 1280x720x81 -> 75,600 tokens (BASELINE configs[3])
+    default_cfg = args.model == "1.3B" and args.attn == "bf16" and args.ffn_bits == 8
     sp = SequenceParallel() if world > 1 else None
-    dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers)
+    dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers, attn_quant=(args.attn == "int8"),
+                           ffn_bits=args.ffn_bits)
     L = (LATENT_SHAPE[1] // 1) * (LATENT_SHAPE[2] // 2) * (LATENT_SHAPE[3] // 2)
 
     g = torch.Generator().manual_seed(0)
@@ -250,14 +263,18 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # the public step: CUDA-graph replay of WanDiTQ.forward (wan.model.GraphedDiT); --no-graph launches eagerly
+    use_graph = not args.no_graph
+    runner = M.GraphedDiT(dit) if use_graph else dit.forward
+
     def step_resident():
-        return dit.forward(lat_d, t_d, ctx_d)
+        return runner(lat_d, t_d, ctx_d)
 
     def step_e2e():
         lat = lat_h.to(dev, non_blocking=True)
         ctx = ctx_h.to(dev, non_blocking=True)
         t = t_h.to(dev, non_blocking=True)
-        y = dit.forward(lat, t, ctx)
+        y = runner(lat, t, ctx)
         out_h.copy_(y, non_blocking=True)
         return y
 
@@ -282,8 +299,6 @@ def run_b200(args):
     clocks = ClockSampler(local) if rank == 0 else None
     if clocks is not None:
         clocks.start()
-    M.qlinear = timed_qlinear
-    launches0 = b200q.launch_count
     sync_all()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
@@ -291,11 +306,24 @@ def run_b200(args):
         step_resident()
     ev1.record()
     sync_all()
-    launches = b200q.launch_count - launches0
-    M.qlinear = orig_qlinear
     ms = ev0.elapsed_time(ev1) / args.steps
 
-    # dominant-kernel accounting
+    # per-kernel pass: the same K steps launched eagerly with CUDA events around every quantized-GEMM launch (events cannot
+    # be read back from inside a replayed graph); also counts this library's launches per step
+    M.qlinear = timed_qlinear
+    launches0 = b200q.launch_count
+    sync_all()
+    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev4.record()
+    for _ in range(args.steps):
+        dit.forward(lat_d, t_d, ctx_d)
+    ev5.record()
+    sync_all()
+    launches = b200q.launch_count - launches0
+    M.qlinear = orig_qlinear
+    eager_ms = ev4.elapsed_time(ev5) / args.steps
+
+    # dominant-kernel accounting: all quantized-GEMM launches, and the single heaviest shape (roofline object)
     g_ms = sum(s.elapsed_time(e) for s, e, _, _ in gemm_events)
     g_ops = sum(o for _, _, o, _ in gemm_events)
     by_shape = {}
@@ -305,6 +333,29 @@ def run_b200(args):
     gemm_events.clear()
 
     clk = clocks.stop() if clocks is not None else None
+
+    # extra timing at N=1 on the headline config: the same step with the fused int8 attention kernel (configs[4] semantics)
+    variants = {}
+    if world == 1 and default_cfg and not args.no_variants and args.layers is None:
+        try:
+            for blk in dit.blocks:
+                blk.attn_quant = True
+            vrun = M.GraphedDiT(dit) if use_graph else dit.forward
+            for _ in range(2):
+                vrun(lat_d, t_d, ctx_d)
+            torch.cuda.synchronize()
+            v0, v1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            v0.record()
+            for _ in range(2):
+                vrun(lat_d, t_d, ctx_d)
+            v1.record()
+            torch.cuda.synchronize()
+            variants["w8a8_linears_int8_attention_ms"] = v0.elapsed_time(v1) / 2
+        except Exception as ex:  # noqa: BLE001
+            variants["w8a8_linears_int8_attention_ms"] = "failed: " + repr(ex)
+        finally:
+            for blk in dit.blocks:
+                blk.attn_quant = False
 
     if world > 1:
         tmax = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
@@ -322,24 +373,48 @@ def run_b200(args):
             peak, peak_src = 2.0 * bf16_sus, "2 x MEASURED_PEAKS.json bf16_tflops_sustained (kind::i8 issues at 2x the bf16 rate)"
         else:
             peak, peak_src = 2.0 * 1400.0, "fallback: 2 x 1.4 PFLOP/s sustained bf16 (B200_PROFILING.md)"
-        achieved = g_ops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        all_tops = g_ops / (g_ms * 1e-3) / 1e12 if g_ms > 0 else 0.0
+        # the dominant launch: the shape with the largest share of GEMM time
+        dom = max(by_shape, key=lambda k: by_shape[k][0]) if by_shape else None
+        dom_ms = by_shape[dom][0] / by_shape[dom][2] if dom else 0.0
+        dom_ops = by_shape[dom][1] / by_shape[dom][2] if dom else 0.0
+        achieved = dom_ops / (dom_ms * 1e-3) / 1e12 if dom_ms > 0 else 0.0
+        traffic = None
+        try:                        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu capture
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("gemm", {}).get(dom)
+        except Exception:  # noqa: BLE001
+            pass
+        metric = METRIC if args.model == "1.3B" else "W8A8 DiT-step ms (Wan2.1-T2V-14B, 40 blocks, 75600 tokens)"
+        workload = WORKLOAD if args.model == "1.3B" else (
+            "Wan2.1-T2V-14B 40-block DiT W8A8 denoising step, 1280x720x81 synthetic latent (16x21x90x160 -> 75600 tokens), "
+            "one CFG branch; BASELINE.json configs[3]")
+        if not default_cfg:
+            workload += f" [attention={args.attn}, ffn weights {args.ffn_bits}-bit]"
         out = {
-            "metric": METRIC, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "metric": metric, "value": ms, "unit": "ms", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms, "higher_is_better": False, "scaling": "strong", "vs_baseline": None,
-            "dtype": "int8 (s32 accumulate, bf16 attention core)", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "parallelism": f"ulysses{world}" if world > 1 else "single-gpu",
+            "dtype": "int8 (s32 accumulate, %s attention core)" % ("bf16 library" if args.attn == "bf16" else "int8 tcgen05"),
+            "data": "synthetic",
+            "config": {"workload": workload, "parallelism": f"ulysses{world}" if world > 1 else "single-gpu",
                        "weights": "random-init, replicated", "l2": "per-step working set (>=200 MB per stage) >> 126 MB L2; no flush needed",
                        "cfg_branches_per_step": 1},
             "clocks": clk,
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": lat_h.numel() * 4 + ctx_h.numel() * 4 + 4,
                     "d2h_bytes_per_step": out_h.numel() * 4},
             "gpu_launches": launches,
-            "roofline": {"bound": "tensor", "kernel": "gemm_i8_kernel (tcgen05.mma.cta_group::2.kind::i8, TMA, TMEM)", "achieved": achieved,
-                         "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None, "traffic": None,
+            "launch_mode": "cuda-graph replay (wan.model.GraphedDiT)" if use_graph else "eager",
+            "eager_ms_per_step": eager_ms,
+            "roofline": {"bound": "tensor", "kernel": f"gemm_i8_kernel M,N,K={dom} (tcgen05.mma.cta_group::2.kind::i8, TMA, TMEM)",
+                         "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,
+                         "traffic": traffic, "algorithmic_ops_per_launch": dom_ops, "avg_launch_ms": dom_ms,
                          "peak_source": peak_src, "frac_of_nominal_4500": achieved / 4500.0,
-                         "gemm_share_of_step": g_ms / (ms * args.steps),
+                         "all_gemms_tops": all_tops, "all_gemms_frac": all_tops / peak if peak else None,
+                         "gemm_share_of_step": g_ms / (eager_ms * args.steps),
+                         "timing": "CUDA events around every GEMM launch in an eagerly launched pass of the same K steps",
                          "by_shape_tops": {k: v[1] / (v[0] * 1e-3) / 1e12 for k, v in by_shape.items() if v[0] > 0}},
         }
+        if variants:
+            out["variants"] = variants
         try:
             out["hbm_kernels"] = hbm_kernel_rates(dev, peaks.get("hbm_gbs"))
         except Exception as ex:  # noqa: BLE001
@@ -357,14 +432,29 @@ def run_b200(args):
             except Exception as ex:  # noqa: BLE001
                 out["cpu_baseline"] = {"value": None, "unit": "ms", "cores": os.cpu_count(), "kind": "port",
                                        "sample": "failed: " + repr(ex)}
-        print(json.dumps(out))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        print(json.dumps(out), flush=True)
+    # No collective and no process-group teardown after the numbers are out: destroying an NCCL communicator whose
+    # send/recvs live inside captured CUDA graphs was observed to hang on B200 (torch 2.11 / NCCL 2.28); every rank has
+    # finished its collectives at this point, so it leaves immediately.
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
+
+
+def _watchdog(seconds):
+    """A benchmark must never hold a GPU box hostage: hard-exit if the run exceeds its wall-clock budget."""
+    def fire():
+        sys.stderr.write(f"bench.py: watchdog fired after {seconds} s - aborting\n")
+        sys.stderr.flush()
+        os._exit(3)
+    t = threading.Timer(seconds, fire)
+    t.daemon = True
+    t.start()
 
 
 if __name__ == "__main__":
     a = parse()
+    _watchdog(a.max_seconds)
     if a.impl == "reference":
         run_reference(a)
     else:
