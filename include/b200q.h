@@ -235,7 +235,9 @@ B200Q_API int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int6
                   b200q_stream_t stream);
 
 /* Scheduling knob of b200q_attn_i8 (debug / benchmarking; results identical): bit 0 = S accumulators pre-initialised
- * with the int->fp32 conversion bias by tcgen05.st, bit 1 = pass 1 hands two key blocks per barrier round trip. */
+ * with the int->fp32 conversion bias by tcgen05.st, bit 1 = pass 1 hands two key blocks per barrier round trip,
+ * bit 2 = a quarter of the softmax exponentials evaluated by a degree-4 polynomial on the FMA/ALU pipes instead of the
+ * MUFU (P~ within 7e-6 relative of the MUFU path; bits 0-1 leave results bit-identical). */
 B200Q_API int b200q_attn_set_mode(int mode);
 
 #ifdef __cplusplus

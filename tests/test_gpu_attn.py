@@ -142,3 +142,14 @@ def test_attn_i8_bad_args(dev):
     with pytest.raises(b200q.B200QError):                     # head_dim 64 is not supported
         b200q.attn_i8(qq, torch.ones(8, 1, device=dev), qq, torch.ones(8, 1, device=dev),
                       torch.zeros(64, 16, dtype=torch.int8, device=dev)[:, :8], torch.ones(64, device=dev), 1)
+
+
+def test_attn_i8_polynomial_exp_mode(dev):
+    """Scheduling mode with a quarter of the exponentials on the FMA/ALU pipes (degree-4 polynomial, 7e-6 relative):
+    same parity bars as the MUFU path — accumulators exact, P~ codes within one step of the float64 codes."""
+    b200q.load().b200q_attn_set_mode(6)
+    try:
+        test_attn_i8_parity(dev, 2, 300, 333)
+        test_attn_i8_parity(dev, 1, 5, 3)
+    finally:
+        b200q.load().b200q_attn_set_mode(2)

@@ -167,6 +167,21 @@ def test_w4a8_gemm(dev, M, N, K, with_zp):
     assert rel <= 2e-5, rel          # exact integer accumulation: only the fp32 epilogue rounds
 
 
+def test_pack_w4_saturates_out_of_range_codes(dev):
+    """The asymmetric 4-bit quantizer can emit +8 on an exact double rounding tie; the packer stores it as +7 (and
+    anything below -8 as -8) instead of letting the nibble wrap to the opposite sign."""
+    M, N, K = 64, 32, 128
+    qa = _codes(M, K, 5)
+    qw = _codes(N, K, 6, -8, 7)
+    qw[3, 10], qw[7, 0], qw[9, 127] = 8, 9, -9
+    clipped = qw.clamp(-8, 7)
+    da, dw = torch.ones(M), torch.ones(N)
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32)
+    out = b200q.gemm_w4a8(qa.to(dev), b200q.pack_w4(qw.to(dev)), K, da.to(dev), dw.to(dev), None, rs.to(dev), None,
+                          out_dtype=torch.float32)
+    assert torch.equal(out.cpu().double(), O.int_accumulators(qa, clipped).double())
+
+
 def test_w4a8_quantized_linear_golden(dev, golden_dir):
     """W4 asym weights / A8 sym activations end to end vs the imported reference QuantizedLinear (fp32 fake-quant)."""
     rec = torch.load(os.path.join(golden_dir, "quantized_linear.pt"))["w4a8"]

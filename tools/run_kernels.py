@@ -20,6 +20,8 @@ qh = torch.randint(-127, 128, (L, Fd), dtype=torch.int8, device=dev)
 w_dd = torch.randint(-128, 128, (D, D), dtype=torch.int8, device=dev)
 w_fd = torch.randint(-128, 128, (Fd, D), dtype=torch.int8, device=dev)
 w_df = torch.randint(-128, 128, (D, Fd), dtype=torch.int8, device=dev)
+w_qkv = torch.randint(-128, 128, (3 * D, D), dtype=torch.int8, device=dev)
+dwq, zq, bq = torch.rand(3 * D, device=dev) * 1e-2, torch.ones(3 * D, device=dev), torch.rand(3 * D, device=dev)
 w4 = b200q.pack_w4(torch.randint(-8, 8, (Fd, D), dtype=torch.int8, device=dev))
 da = torch.rand(L, device=dev) * 1e-2
 rs = torch.randint(-1000, 1000, (L,), dtype=torch.int32, device=dev)
@@ -40,5 +42,13 @@ for _ in range(3):
     b200q.gemm_w8a8(qh, w_df, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # F->D
     b200q.gemm_w8a8(qa, w_dd, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # D->D gate
     b200q.gemm_w4a8(qa, w4, D, da, dwf, zf, rs, bf)
+    b200q.gemm_w8a8(qa, w_qkv, da, dwq, zq, rs, bq)                                            # D->3D (q|k|v), bf16 out
+# quantized attention path (configs[4]): fused Q/K quantizer, V^T quantizer, int8 attention (H=12, L=32760)
+H = 12
+for _ in range(2):
+    qq, dq, _ = b200q.rmsnorm_rope_quant(qkv[:, :D], dwd, 1e-6, cos, sin, 128)
+    kq, dk, _ = b200q.rmsnorm_rope_quant(qkv[:, D:2 * D], dwd, 1e-6, cos, sin, 128)
+    vt, dv = b200q.quant_vt(qkv[:, 2 * D:], 8)
+    b200q.attn_i8(qq, dq, kq, dk, vt, dv, H)
 torch.cuda.synchronize()
 print("ok", b200q.launch_count)

@@ -45,6 +45,23 @@ if os.path.exists(rep):
                     f.write(f"| {label} (`{key}`) | {r[col[key]]} {units[col[key]]} |\n")
             f.write("\n")
     print("wrote", f"{tag}_ncu_full_summary.md")
+    # dram traffic per launch of the GEMMs, keyed by shape: tools/run_kernels.py launches them in this order
+    import json
+    order = ["32760x1536x1536", "32760x8960x1536", "32760x1536x8960", "32760x1536x1536_gate", "32760x8960x1536_w4a8",
+             "32760x4608x1536"]
+    gemm_rows = [r for r in rows[2:] if "gemm_i8_kernel" in r[col["Kernel Name"]]]
+    def to_bytes(r, key):
+        v = float(r[col[key]].replace(",", ""))
+        return v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(units[col[key]], 1)
+    traffic = {"source": f"profiles/{tag}_ncu_full_summary.md (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+               "gemm": {}, "gemm_duration_us": {}}
+    for name, r in zip(order, gemm_rows[:len(order)]):
+        traffic["gemm"][name] = to_bytes(r, "dram__bytes_read.sum") + to_bytes(r, "dram__bytes_write.sum")
+    attn_rows = [r for r in rows[2:] if "attn_i8_kernel" in r[col["Kernel Name"]]]
+    if attn_rows:
+        traffic["attn_i8_H12_L32760"] = to_bytes(attn_rows[0], "dram__bytes_read.sum") + to_bytes(attn_rows[0], "dram__bytes_write.sum")
+    json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
+    print("wrote traffic.json", traffic["gemm"])
 
 if os.path.exists(launches):
     lines = [l for l in open(launches) if not l.startswith("==")]
@@ -61,8 +78,8 @@ if os.path.exists(launches):
     tot = sum(v[1] for v in agg.values())
     with open(os.path.join(out_dir, f"{tag}_launches_by_kernel.md"), "w") as f:
         f.write(f"# ncu --metrics gpu__time_duration.sum --clock-control none — {os.path.basename(launches)}\n\n")
-        f.write("Command: `python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline` (2 of 30 blocks so the "
-                "listing stays short; per-block shares are those of the full step).\n\n")
+        f.write("Command: `python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-variants` (2 of 30 "
+                "blocks so the listing stays short; per-block shares are those of the full step).\n\n")
         f.write(f"{sum(v[0] for v in agg.values())} launches, {tot / 1e6:.3f} ms of kernel time.\n\n")
         f.write("| ms | share | launches | kernel |\n|---:|---:|---:|---|\n")
         for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:40]:

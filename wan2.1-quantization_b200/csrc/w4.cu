@@ -21,8 +21,11 @@ __global__ void __launch_bounds__(256) pack_w4_kernel(const int8_t* __restrict__
 #pragma unroll
     for (int b = 0; b < 4; ++b) {
       const int64_t k0 = g * 8 + b, k1 = g * 8 + 4 + b;
-      const uint32_t lo = k0 < K ? (uint32_t)(src[b] + 8) & 0xF : 8u;       // pad codes are 0 -> nibble 8
-      const uint32_t hi = k1 < K ? (uint32_t)(src[4 + b] + 8) & 0xF : 8u;
+      // saturate to [-8, 7]: the asymmetric quantizer can emit +8 on an exact double rounding tie (rne(xmax/d) and
+      // rne(xmin/d) both rounding outward) - a 17th level that 4 bits cannot hold; without the clamp
+      // the nibble would wrap to -8.  Same policy as the int8 storage of 8-bit codes (+128 -> +127).
+      const uint32_t lo = k0 < K ? (uint32_t)(min(max((int)src[b], -8), 7) + 8) : 8u;       // pad codes are 0 -> nibble 8
+      const uint32_t hi = k1 < K ? (uint32_t)(min(max((int)src[4 + b], -8), 7) + 8) : 8u;
       w |= (lo | (hi << 4)) << (8 * b);
     }
     *reinterpret_cast<uint32_t*>(packed + n * ldp + g * 4) = w;
