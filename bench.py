@@ -49,7 +49,7 @@ def parse():
                     help="attention core: library bf16 flash attention (configs[1]) or the fused int8 Q.K^T/P.V kernel (configs[4])")
     ap.add_argument("--ffn-bits", type=int, default=8, choices=[4, 8], help="4 = W4A8 FFN weights (configs[4])")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra int8-attention timing at N=1")
-    ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: hard-exit after this wall-clock time")
+    ap.add_argument("--max-seconds", type=float, default=600.0, help="watchdog: hard-exit after this wall-clock time")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 

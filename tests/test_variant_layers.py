@@ -60,7 +60,9 @@ def _check(layer, rec, device="cpu"):
     # activation codes can flip by one step where the fp32 Hadamard transform and the reference's fp64 matmul round
     # differently; one flipped code moves an output by delta_a*|w| ~ 1e-3 of the output scale
     rel = float((y - ref).abs().max() / ref.abs().max())
-    assert rel <= 5e-3, rel
+    # 4-bit: a weight whose reference code is the unrepresentable +8 (exact double tie) is stored as +7, one 4-bit
+    # step (1/15 of the row range) off - measured 6.3e-3 on viditq_w4
+    assert rel <= (5e-3 if rec["w_bits"] == 8 else 2e-2), rel
     cos = float((y.double().flatten() @ ref.double().flatten()) / (y.double().norm() * ref.double().norm()))
     assert cos >= 0.99999, cos
 
