@@ -212,8 +212,8 @@ def hbm_kernel_rates(dev, peak_gbs):
 def run_b200(args):
     import torch.distributed as dist
     import b200q
-    from wan import model as M
-    from wan.parallel import SequenceParallel, exchange_bytes_per_rank
+    from wan_b200 import model as M
+    from wan_b200.parallel import SequenceParallel, exchange_bytes_per_rank
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -263,7 +263,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # the public step: CUDA-graph replay of WanDiTQ.forward (wan.model.GraphedDiT); --no-graph launches eagerly
+    # the public step: CUDA-graph replay of WanDiTQ.forward (wan_b200.model.GraphedDiT); --no-graph launches eagerly
     use_graph = not args.no_graph
     runner = M.GraphedDiT(dit) if use_graph else dit.forward
 
@@ -402,7 +402,7 @@ def run_b200(args):
             "e2e": {"value": e2e_ms, "unit": "ms", "h2d_bytes_per_step": lat_h.numel() * 4 + ctx_h.numel() * 4 + 4,
                     "d2h_bytes_per_step": out_h.numel() * 4},
             "gpu_launches": launches,
-            "launch_mode": "cuda-graph replay (wan.model.GraphedDiT)" if use_graph else "eager",
+            "launch_mode": "cuda-graph replay (wan_b200.model.GraphedDiT)" if use_graph else "eager",
             "eager_ms_per_step": eager_ms,
             "roofline": {"bound": "tensor", "kernel": f"gemm_i8_kernel M,N,K={dom} (tcgen05.mma.cta_group::2.kind::i8, TMA, TMEM)",
                          "achieved": achieved, "peak": peak, "unit": "TOP/s", "frac": achieved / peak if peak else None,

@@ -222,7 +222,7 @@ B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, 
  *   query row); O = (P~q.vtq^T) exact in int32 * dv / (255 * sum_j P~).  out bf16 [Lq, H*128] (ldo).
  *   Deviation from the reference's attention-map grouping ('row': one scale per KEY column over all queries,
  *   quant_attn.py:168-174), which needs the whole [L, L] map first: see DESIGN.md; the parity path for that grouping is
- *   wan/attention_q.py (small L).
+ *   wan_b200/attention_q.py (small L).
  *   Optional debug/parity outputs (NULL to skip): m_out, l_out fp32 [H, Lq] (row maximum in log2 units, row sum of P~);
  *   p_out uint8 [H, Lq, ldp] (P~ codes; ldp multiple of 16 and >= ceil(Lk/128)*128); acc_out int32 [Lq, ldacc]
  *   (raw P.V accumulators).  Lk <= 66,000 (int32 accumulator bound). */

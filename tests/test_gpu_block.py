@@ -6,7 +6,7 @@ import torch
 
 import b200q
 from oracle import fakequant_oracle as O
-from wan import model as M
+from wan_b200 import model as M
 
 pytestmark = pytest.mark.gpu
 
@@ -64,7 +64,7 @@ def test_dit_forward_runs_and_is_deterministic(dev):
 
 def test_calibration_collector(dev):
     import torch.nn as nn
-    from wan.calibration import CalibrationCollector
+    from wan_b200.calibration import CalibrationCollector
     m = nn.Sequential(nn.Linear(64, 128), nn.GELU(), nn.Linear(128, 32)).to(dev)
     col = CalibrationCollector(m)
     xs = [torch.randn(3, 50, 64, device=dev) * (i + 1) for i in range(3)]
@@ -102,7 +102,7 @@ def test_quantized_attention_parity_mode(dev, golden_dir):
     imported reference quantizers: Q/K/V deltas and dequantised tensors bit-exact; P codes within one step (S comes
     from the int8 GEMM's fp32 epilogue instead of an fp32 matmul); output cosine >= 0.9999."""
     import os
-    from wan.attention_q import quantized_attention_parity
+    from wan_b200.attention_q import quantized_attention_parity
     rec = torch.load(os.path.join(golden_dir, "quant_attention.pt"))
     B, H, L, hd = rec["q"].shape
     to_tok = lambda t: t[0].permute(1, 0, 2).reshape(L, H * hd).contiguous().to(dev)      # [1,H,L,hd] -> [L, H*hd]

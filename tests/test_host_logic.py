@@ -143,11 +143,17 @@ def test_mixed_precision_bitwidth_refactor(monkeypatch):
     assert torch.equal(ffn.weight.data, O.fake_quant_rows(ffn.fp_weight.detach(), 4, False, dynamic=False))
 
 
-def test_method_sections_fail_loudly_until_built(monkeypatch):
+def test_method_sections_select_the_variant_layers(monkeypatch):
+    """The shipped YAML's `viditq:` section with `layer_name_regex: ""` selects ViDiTQuantizedLinear for every quantized
+    layer (quant_configs/config.yaml:19-21, quant_model.py:45-53); a layer without its PTQ state refuses to run."""
     fake_backend.install(monkeypatch)
+    from qdiff.viditq.viditq_quant_layer import ViDiTQuantizedLinear
     m = Tiny()
-    with pytest.raises(NotImplementedError):
-        _refactor(m, _cfg(viditq={"alpha": 0.5665, "layer_name_regex": ""}))
+    _refactor(m, _cfg(viditq={"alpha": 0.5665, "layer_name_regex": ""}))
+    assert isinstance(m.blocks[0].self_attn.q, ViDiTQuantizedLinear)
+    assert isinstance(m.blocks[0].self_attn.o, nn.Linear) and not isinstance(m.blocks[0].self_attn.o, ViDiTQuantizedLinear)
+    with pytest.raises(RuntimeError):
+        m.blocks[0].self_attn.q(torch.randn(1, 4, 32))      # channel_mask / rotation not set yet
 
 
 def test_quantizers_refuse_to_run_without_a_gpu():

@@ -68,7 +68,7 @@ def _quantize(model, w_bits=8):
 
 def test_export_schema_cpu(monkeypatch):
     fake_backend.install(monkeypatch)
-    from wan import int_checkpoint as IC
+    from wan_b200 import int_checkpoint as IC
     from oracle import fakequant_oracle as O
     torch.manual_seed(0)
     m = _quantize(TinyWan(d=32, f=64))
@@ -88,8 +88,8 @@ def test_export_schema_cpu(monkeypatch):
 
 @pytest.mark.gpu
 def test_save_load_roundtrip_gpu(dev, tmp_path):
-    from wan import int_checkpoint as IC
-    from wan import model as M
+    from wan_b200 import int_checkpoint as IC
+    from wan_b200 import model as M
     torch.manual_seed(0)
     d, f = 256, 512
     m = _quantize(TinyWan(d=d, f=f, layers=2).to(dev))
@@ -107,3 +107,57 @@ def test_save_load_roundtrip_gpu(dev, tmp_path):
     lat = torch.randn(16, 2, 8, 12, device=dev, generator=g)
     y = dit.forward(lat, torch.tensor([300.0], device=dev), torch.randn(20, 64, device=dev, generator=g))
     assert y.shape == lat.shape and torch.isfinite(y).all()
+
+
+class _TinyQuantWan(TinyWan):
+    pass
+
+
+def test_quant_wan_mixin_surface_cpu(monkeypatch):
+    """QuantWanModel's method surface (quant_wanx.py:80-185) through the mixin: refactor, param dict round trip, export."""
+    fake_backend.install(monkeypatch)
+    from wan_b200.quant_wanx import QuantWanMixin
+    from qdiff.base.quant_layer import QuantizedLinear
+
+    class M(QuantWanMixin, TinyWan):
+        pass
+    torch.manual_seed(0)
+    m = M(d=32, f=64)
+    m.convert_quant(OmegaConf.create({"remain_fp_regex": REGEX, "weight": {"n_bits": 8, "sym": False},
+                                      "act": {"n_bits": 8, "sym": True}}))
+    assert isinstance(m.blocks[0].ffn[0], QuantizedLinear) and not isinstance(m.text_embedding[0], QuantizedLinear)
+    m.save_quant_param_dict()
+    assert "blocks.0.self_attn.q.w_quantizer" in m.quant_param_dict
+    saved = {k: dict(v) for k, v in m.quant_param_dict.items()}
+    m.load_quant_param_dict(saved)
+    m.set_init_done()
+    assert m.blocks[0].ffn[2].a_quantizer.init_done is True
+    cfg = m.wan_config()
+    assert (cfg.dim, cfg.ffn_dim, cfg.num_layers, cfg.text_dim, cfg.freq_dim) == (32, 64, 1, 64, 64)
+
+
+@pytest.mark.gpu
+def test_hardware_forward_refactor_gpu(dev, tmp_path):
+    """quantize_and_save_weight -> hardware_forward_refactor (quant_wanx.py:137-228): forward() runs on the integer
+    runtime with WanModel's call convention, eager and CUDA-graph replay agree bit for bit."""
+    from wan_b200.quant_wanx import QuantWanMixin
+
+    class M(QuantWanMixin, TinyWan):
+        pass
+    torch.manual_seed(0)
+    m = M(d=256, f=512, layers=2).to(dev)
+    m.convert_quant(OmegaConf.create({"remain_fp_regex": REGEX, "weight": {"n_bits": 8, "sym": False},
+                                      "act": {"n_bits": 8, "sym": True}}))
+    path = os.path.join(tmp_path, "int_weight.pt")
+    m.quantize_and_save_weight(path)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lat = torch.randn(16, 2, 8, 12, device=dev, generator=g)
+    ctx = torch.randn(20, 64, device=dev, generator=g)
+    t = torch.tensor([300.0], device=dev)
+    m.hardware_forward_refactor(path, seq_len=48, use_graph=False)
+    y_eager = m([lat], t, [ctx], 48)[0].clone()
+    m.hardware_forward_refactor(path, seq_len=48, use_graph=True)
+    y_graph = m([lat], t, [ctx], 48)[0].clone()
+    y_graph2 = m([lat], t, [ctx], 48)[0].clone()          # second call replays the captured graph
+    assert y_eager.shape == lat.shape and torch.isfinite(y_eager).all()
+    assert torch.equal(y_eager, y_graph) and torch.equal(y_graph, y_graph2)

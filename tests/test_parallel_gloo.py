@@ -1,4 +1,4 @@
-"""CPU suite, world_size 2 and 4 over gloo: the sequence-parallel attention exchange (wan/parallel.py) reproduces
+"""CPU suite, world_size 2 and 4 over gloo: the sequence-parallel attention exchange (wan_b200/parallel.py) reproduces
 single-process attention exactly (pure permutation + the same attention core), including the P = Pu x Pr hybrid used
 when the head count does not divide by P, and the calibration allreduce(MAX) equals the unsharded statistic."""
 import os
@@ -31,7 +31,7 @@ def _worker(rank, world, port, heads, L, hd, out_q):
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
-    from wan.parallel import SequenceParallel
+    from wan_b200.parallel import SequenceParallel
     torch.manual_seed(0)
     D = heads * hd
     q, k, v = (torch.randn(L, D) for _ in range(3))
@@ -68,7 +68,7 @@ def test_sequence_parallel_attention_gloo(world, heads):
 
 
 def test_head_plan():
-    from wan.parallel import _largest_head_divisor, exchange_bytes_per_rank
+    from wan_b200.parallel import _largest_head_divisor, exchange_bytes_per_rank
     assert _largest_head_divisor(8, 12) == 4 and _largest_head_divisor(4, 12) == 4 and _largest_head_divisor(8, 40) == 8
     b, pu, pr = exchange_bytes_per_rank(75600, 5120, 8, 40)
     assert (pu, pr) == (8, 1)

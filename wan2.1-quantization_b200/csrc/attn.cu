@@ -21,7 +21,7 @@
 //   pass 2: S tiles again -> P~ codes -> shared memory (SWIZZLE_128B, the A operand of P.V) -> O += P~q.Vq
 // The reference's own attention-map grouping ('row' = one scale per KEY column over all queries, quant_attn.py:168-174)
 // needs the complete [L, L] map before the first code can be produced; it is kept as the small-L parity path
-// (wan/attention_q.py) and this kernel is the fast mode, reported as such in DESIGN.md.
+// (wan_b200/attention_q.py) and this kernel is the fast mode, reported as such in DESIGN.md.
 //
 // CTA = 256 queries of one head (two 128-row Q tiles), 384 threads, persistent over (head, q-tile-pair) work items:
 //   warps 0-3 / 4-7  softmax warpgroup of Q tile 0 / 1: thread = one query row = one TMEM lane

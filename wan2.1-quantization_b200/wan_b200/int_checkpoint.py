@@ -116,7 +116,7 @@ def _qweight(sd, name, device):
 
 
 def dit_from_int_state_dict(cfg: WanConfig, sd: dict, device=None, sp=None, attn_quant=False) -> WanDiTQ:
-    """Build the integer runtime (wan.model.WanDiTQ) from an int-weight state dict: the counterpart of
+    """Build the integer runtime (wan_b200.model.WanDiTQ) from an int-weight state dict: the counterpart of
     hardware_forward_refactor's step (3) (quant_wanx.py:221-228).  FP parts (patch/text/time embeddings, head) are taken
     as stored (remain_fp_regex keeps them FP, quant_configs/config.yaml:9)."""
     dev = device or torch.device("cuda", torch.cuda.current_device())

@@ -16,7 +16,7 @@ all ten linears of a block are integer GEMMs and every token-local stage is one 
       ln_mod_quant(norm2, e3/e4) -> gemm + GELU epilogue -> quant_rows -> gemm with epilogue x += y*e5
 
 Sequence parallelism (Ulysses, wan/distributed/xdit_context_parallel.py:66-192): every stage above is token-local,
-so ranks own contiguous token chunks and only attention exchanges data (wan/parallel.py).
+so ranks own contiguous token chunks and only attention exchanges data (wan_b200/parallel.py).
 
 Numerics contract (SURVEY §8a-5): int8 codes and int32 accumulators are bit-exact w.r.t. the fake-quant oracle;
 bf16 block outputs agree to cosine >= 0.999.
