@@ -8,6 +8,8 @@
  *                       (SURVEY appendix A); kernels/bench/bench_gemm.py:27-29 states the same algebra
  *   div_hoisted_check   the row-shared-reciprocal quotient used by the CUDA quantizer
  *                       (wan2.1-quantization_b200/csrc/common.cuh: div_rn_hoisted) against IEEE division
+ *   attn_rowstep_i8     examples/Wan2.1/models/quant_opensora.py:430-478 in its integer form with the row-step
+ *                       attention-map grid of base_quantizer.py:197-199 (the fused attention kernel's semantics)
  * Build with -ffp-contract=off: every '/' must stay an IEEE fp32 division, fmaf the only fused op.
  */
 #include <math.h>
@@ -88,4 +90,39 @@ long div_hoisted_check(long trials, uint64_t seed) {
     }
   }
   return bad;
+}
+
+/* Fused int8 attention in its integer form (what wan2.1-quantization_b200/csrc/attn.cu computes), one head:
+ *   S = qq.kq^T exact in int32 ; x = S*dq[i]*dk[j]*scale ; P~ = exp(x - rowmax x) ; codes = rint(255*P~) in [0,255]
+ *   (= DynamicQuantizer.forward_with_quant_params' unsigned grid, base_quantizer.py:197-199, delta = row maximum of the
+ *   softmax: P = P~/l, rowmax P = 1/l) ; acc = codes . vq (exact integer) ; out = acc*dv[c] / (255*l), l = sum_j P~.
+ * Follows quant_opensora.py:430-478 for the q/k/v operands (codes and scales are inputs here) and :456-462 for the
+ * softmax; evaluated in double so that the codes are the correctly rounded ones the GPU test compares against.
+ * qq [Lq,hd], kq [Lk,hd], vt [hd,Lk] int8 ; dq [Lq], dk [Lk], dv [hd] ; codes [Lq,Lk] ; acc [Lq,hd] ; out [Lq,hd]. */
+void attn_rowstep_i8(const int8_t* qq, const int8_t* kq, const int8_t* vt, const float* dq, const float* dk, const float* dv,
+                     long Lq, long Lk, long hd, double scale, uint8_t* codes, int64_t* acc, float* out, double* l_out) {
+#pragma omp parallel for schedule(static)
+  for (long i = 0; i < Lq; ++i) {
+    double m = -INFINITY;
+    double* x = (double*)__builtin_alloca(sizeof(double) * (size_t)Lk);
+    for (long j = 0; j < Lk; ++j) {
+      int32_t s = 0;
+      for (long k = 0; k < hd; ++k) s += (int32_t)qq[i * hd + k] * (int32_t)kq[j * hd + k];
+      x[j] = (double)s * (double)dq[i] * (double)dk[j] * scale;
+      if (x[j] > m) m = x[j];
+    }
+    double l = 0.0;
+    for (long j = 0; j < Lk; ++j) {
+      const double p = exp(x[j] - m);
+      l += p;
+      codes[i * Lk + j] = (uint8_t)rint(255.0 * p);
+    }
+    for (long c = 0; c < hd; ++c) {
+      int64_t a = 0;
+      for (long j = 0; j < Lk; ++j) a += (int64_t)codes[i * Lk + j] * (int64_t)vt[c * Lk + j];
+      acc[i * hd + c] = a;
+      out[i * hd + c] = (float)((double)a * (double)dv[c] / (255.0 * l));
+    }
+    if (l_out) l_out[i] = l;
+  }
 }

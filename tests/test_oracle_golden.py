@@ -133,3 +133,29 @@ def test_hoisted_division_is_ieee_division(clib):
     """The CUDA quantizer replaces x/delta by a reciprocal + two exact-remainder corrections (FFMA2); this is the
     same sequence on the CPU (fmaf) against true IEEE division on 16M random / near-tie cases: zero mismatches."""
     assert clib.div_hoisted_check(2_000_000, 12345) == 0
+
+
+def test_c_oracle_attention_rowstep(golden_dir, clib):
+    """The integer form of the fused attention (C, double-precision softmax) against the golden vectors of the imported
+    reference quantizers: codes within one step of the reference's fp32-softmax codes (ties only), outputs to 1e-3."""
+    rec = _load(golden_dir, "quant_attention_rowstep.pt")
+    _, info = O.quantized_attention_rowstep(rec["q"], rec["k"], rec["v"])
+    B, H, Lq, hd = rec["q"].shape
+    Lk = rec["k"].shape[2]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    step = rec["attn"].max(dim=-1, keepdim=True)[0] / 255.0
+    ref_codes = torch.round(rec["attn_quant"] / step)[0]
+    for h in range(H):
+        qq = np.ascontiguousarray(info["qq"][0, h].numpy().astype(np.int8))
+        kq = np.ascontiguousarray(info["kq"][0, h].numpy().astype(np.int8))
+        vt = np.ascontiguousarray(info["vq"][0, h].numpy().astype(np.int8))            # [hd, Lk]
+        dq = np.ascontiguousarray(info["dq"][0, h].numpy()); dk = np.ascontiguousarray(info["dk"][0, h].numpy())
+        dv = np.ascontiguousarray(info["dv"][0, h].numpy())
+        codes = np.empty((Lq, Lk), np.uint8); acc = np.empty((Lq, hd), np.int64); out = np.empty((Lq, hd), np.float32)
+        clib.attn_rowstep_i8(p(qq), p(kq), p(vt), p(dq), p(dk), p(dv), ctypes.c_long(Lq), ctypes.c_long(Lk), ctypes.c_long(hd),
+                             ctypes.c_double(hd ** -0.5), p(codes), p(acc), p(out), None)
+        d = np.abs(codes.astype(np.int32) - ref_codes[h].numpy().astype(np.int32))
+        assert d.max() <= 1 and (d > 0).mean() < 0.01
+        assert np.array_equal(acc, codes.astype(np.int64) @ vt.astype(np.int64).T)
+        ref_out = rec["out"][0, h].numpy()
+        assert np.abs(out - ref_out).max() <= 1e-3 * np.abs(ref_out).max() + 1e-6
