@@ -308,28 +308,71 @@ def run_b200(args):
     sync_all()
     ms = ev0.elapsed_time(ev1) / args.steps
 
-    # per-kernel pass: the same K steps launched eagerly with CUDA events around every quantized-GEMM launch (events cannot
-    # be read back from inside a replayed graph); also counts this library's launches per step
-    M.qlinear = timed_qlinear
+    # per-kernel pass.  Preferred: the same K steps replayed from a second CUDA graph that carries an external timing
+    # event (cudaEventRecordExternal) before and after every quantized-GEMM launch, so the per-launch durations are free
+    # of host launch gaps.  Fallback (if that capture is refused): eager launches with ordinary events.
+    per_kernel_mode = "cuda-graph replay with external event-record nodes around every GEMM launch"
+    pool, cursor = [], [0]
+
+    def timed_qlinear_ext(qa, da, rowsum, w, *a, **kw):
+        i = cursor[0]
+        cursor[0] += 1
+        if i == len(pool):
+            pool.append((torch.cuda.Event(enable_timing=True, external=True), torch.cuda.Event(enable_timing=True, external=True),
+                         2.0 * qa.shape[0] * w.N * w.K, (qa.shape[0], w.N, w.K)))
+        s, e, _, _ = pool[i]
+        s.record()
+        y = orig_qlinear(qa, da, rowsum, w, *a, **kw)
+        e.record()
+        return y
+
+    class _Counted:
+        def forward(self, *a):
+            cursor[0] = 0
+            return dit.forward(*a)
+
     launches0 = b200q.launch_count
-    sync_all()
-    ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev4.record()
-    for _ in range(args.steps):
-        dit.forward(lat_d, t_d, ctx_d)
-    ev5.record()
-    sync_all()
-    launches = b200q.launch_count - launches0
-    M.qlinear = orig_qlinear
-    eager_ms = ev4.elapsed_time(ev5) / args.steps
+    dit.forward(lat_d, t_d, ctx_d)
+    launches = (b200q.launch_count - launches0) * args.steps       # this library's launches per step x K
+    eager_ms = None
+    try:
+        if not use_graph:
+            raise RuntimeError("--no-graph")
+        M.qlinear = timed_qlinear_ext
+        inst = M.GraphedDiT(_Counted())
+        inst(lat_d, t_d, ctx_d)
+        sync_all()
+        if inst.failed is not None:
+            raise RuntimeError(inst.failed)
+        for _ in range(args.steps):
+            inst(lat_d, t_d, ctx_d)
+            torch.cuda.synchronize()
+            for s_, e_, o_, shp_ in pool:
+                gemm_events.append((s_.elapsed_time(e_), o_, shp_))
+        M.qlinear = orig_qlinear
+        del inst
+    except Exception as ex:  # noqa: BLE001
+        per_kernel_mode = "eager launches, CUDA events around every GEMM launch (graph instrumentation failed: %r)" % (ex,)
+        gemm_events.clear()
+        M.qlinear = timed_qlinear
+        sync_all()
+        ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev4.record()
+        for _ in range(args.steps):
+            dit.forward(lat_d, t_d, ctx_d)
+        ev5.record()
+        sync_all()
+        M.qlinear = orig_qlinear
+        eager_ms = ev4.elapsed_time(ev5) / args.steps
+        gemm_events[:] = [(s_.elapsed_time(e_), o_, shp_) for s_, e_, o_, shp_ in gemm_events]
 
     # dominant-kernel accounting: all quantized-GEMM launches, and the single heaviest shape (roofline object)
-    g_ms = sum(s.elapsed_time(e) for s, e, _, _ in gemm_events)
-    g_ops = sum(o for _, _, o, _ in gemm_events)
+    g_ms = sum(t_ for t_, _, _ in gemm_events)
+    g_ops = sum(o for _, o, _ in gemm_events)
     by_shape = {}
-    for s, e, o, shp in gemm_events:
+    for t_, o, shp in gemm_events:
         a = by_shape.setdefault("x".join(map(str, shp)), [0.0, 0.0, 0])
-        a[0] += s.elapsed_time(e); a[1] += o; a[2] += 1
+        a[0] += t_; a[1] += o; a[2] += 1
     gemm_events.clear()
 
     clk = clocks.stop() if clocks is not None else None
@@ -409,8 +452,8 @@ def run_b200(args):
                          "traffic": traffic, "algorithmic_ops_per_launch": dom_ops, "avg_launch_ms": dom_ms,
                          "peak_source": peak_src, "frac_of_nominal_4500": achieved / 4500.0,
                          "all_gemms_tops": all_tops, "all_gemms_frac": all_tops / peak if peak else None,
-                         "gemm_share_of_step": g_ms / (eager_ms * args.steps),
-                         "timing": "CUDA events around every GEMM launch in an eagerly launched pass of the same K steps",
+                         "gemm_share_of_step": g_ms / ((eager_ms or ms) * args.steps),
+                         "timing": per_kernel_mode,
                          "by_shape_tops": {k: v[1] / (v[0] * 1e-3) / 1e12 for k, v in by_shape.items() if v[0] > 0}},
         }
         if variants:
