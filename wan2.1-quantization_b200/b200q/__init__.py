@@ -360,11 +360,27 @@ def quant_vt(v, n_bits=8):
     return buf[:, :Lk], delta
 
 
-def attn_i8(qq, dq, kq, dk, vtq, dv, num_heads, sm_scale=None, out=None, debug=False):
+ATTN_MAX_KEYS = 65536        # int32 P.V accumulator bound of one kernel call: Lk * 255 * 127 < 2^31
+
+
+def _attn_i8_call(qq, dq, kq, dk, vtq, dv, H, hd, sm_scale, out, m, l, pc, ldp, acc):
+    Lq, Lk = qq.shape[0], kq.shape[0]
+    rc = load().b200q_attn_i8(_ptr(qq), _ld(qq), _ptr(dq), dq.stride(0), dq.stride(1), _ptr(kq), _ld(kq), _ptr(dk),
+                              dk.stride(0), dk.stride(1), _ptr(vtq), _ld(vtq), _ptr(dv), Lq, Lk, H, hd, sm_scale,
+                              _ptr(out), BF16, _ld(out), _ptr(m), _ptr(l), _ptr(pc), ldp, _ptr(acc),
+                              _ld(acc) if acc is not None else 0, _stream())
+    _check(rc, "b200q_attn_i8")
+
+
+def attn_i8(qq, dq, kq, dk, vtq, dv, num_heads, sm_scale=None, out=None, debug=False, max_keys=None):
     """Fused int8 attention (include/b200q.h).  qq [Lq, H*128] int8, dq [Lq, H] f32 (any strides), kq/dk likewise,
     vtq [H*128, Lk] int8 (row pitch multiple of 16), dv [H*128] f32 -> bf16 [Lq, H*128].
     debug=True also returns dict(m, l, p, acc): row max (log2 units) / row sum [H, Lq], P~ codes uint8 [H, Lq, Lk],
-    raw int32 P.V accumulators [Lq, H*128]."""
+    raw int32 P.V accumulators [Lq, H*128].
+    Lk > max_keys (default 65,536: the int32 accumulator bound; Wan-14B at 1280x720 has 75,600 keys): the keys are split
+    into chunks, each chunk is one kernel call with its own row maximum, and the partial outputs are merged with the
+    log-sum-exp weights l_c * 2^(m_c - m) (the flash-attention split-K identity); the attention-map grid is then one step
+    per (query row, key chunk)."""
     for t, n in ((qq, "qq"), (dq, "dq"), (kq, "kq"), (dk, "dk"), (vtq, "vtq"), (dv, "dv")):
         _cuda(t, n)
     Lq, D = qq.shape
@@ -376,6 +392,31 @@ def attn_i8(qq, dq, kq, dk, vtq, dv, num_heads, sm_scale=None, out=None, debug=F
     sm_scale = hd ** -0.5 if sm_scale is None else float(sm_scale)
     dev = qq.device
     out = torch.empty((Lq, D), dtype=torch.bfloat16, device=dev) if out is None else out
+    dv = dv.contiguous()
+    max_keys = ATTN_MAX_KEYS if max_keys is None else int(max_keys)
+    if Lk > max_keys:
+        if debug:
+            raise B200QError("attn_i8: debug outputs are per kernel call; not available when the keys are split")
+        n_chunks = -(-Lk // max_keys)
+        step = -(-Lk // n_chunks)
+        step = (step + 127) // 128 * 128                       # chunk starts stay 16-byte aligned inside vtq rows
+        parts = []
+        for k0 in range(0, Lk, step):
+            k1 = min(Lk, k0 + step)
+            o_c = torch.empty((Lq, D), dtype=torch.bfloat16, device=dev)
+            m_c = torch.empty((H, Lq), dtype=torch.float32, device=dev)
+            l_c = torch.empty((H, Lq), dtype=torch.float32, device=dev)
+            _attn_i8_call(qq, dq, kq[k0:k1], dk[k0:k1], vtq[:, k0:k1], dv, H, hd, sm_scale, o_c, m_c, l_c, None, 0, None)
+            parts.append((o_c, m_c, l_c))
+        m = torch.stack([p[1] for p in parts]).amax(dim=0)                        # [H, Lq], log2 units
+        w = [p[2] * torch.exp2(p[1] - m) for p in parts]                          # l_c * 2^(m_c - m)
+        tot = sum(w)
+        acc = None
+        for (o_c, _, _), w_c in zip(parts, w):
+            term = o_c.view(Lq, H, hd).float() * (w_c / tot).t().unsqueeze(-1)
+            acc = term if acc is None else acc + term
+        out.copy_(acc.view(Lq, D))
+        return out
     m = l = pc = acc = None
     ldp = 0
     if debug:
@@ -384,12 +425,7 @@ def attn_i8(qq, dq, kq, dk, vtq, dv, num_heads, sm_scale=None, out=None, debug=F
         ldp = (Lk + 127) // 128 * 128
         pc = torch.zeros((H, Lq, ldp), dtype=torch.uint8, device=dev)
         acc = torch.empty((Lq, D), dtype=torch.int32, device=dev)
-    dv = dv.contiguous()
-    rc = load().b200q_attn_i8(_ptr(qq), _ld(qq), _ptr(dq), dq.stride(0), dq.stride(1), _ptr(kq), _ld(kq), _ptr(dk),
-                              dk.stride(0), dk.stride(1), _ptr(vtq), _ld(vtq), _ptr(dv), Lq, Lk, H, hd, sm_scale,
-                              _ptr(out), BF16, _ld(out), _ptr(m), _ptr(l), _ptr(pc), ldp, _ptr(acc),
-                              _ld(acc) if acc is not None else 0, _stream())
-    _check(rc, "b200q_attn_i8")
+    _attn_i8_call(qq, dq, kq, dk, vtq, dv, H, hd, sm_scale, out, m, l, pc, ldp, acc)
     if debug:
         return out, dict(m=m, l=l, p=pc[:, :, :Lk], acc=acc)
     return out
