@@ -338,6 +338,9 @@ def run_b200(args):
     try:
         if not use_graph:
             raise RuntimeError("--no-graph")
+        if world > 1:
+            # validated on one GPU only; a capture that failed on a single rank would leave the others inside NCCL
+            raise RuntimeError("multi-rank run: per-kernel pass launched eagerly")
         M.qlinear = timed_qlinear_ext
         inst = M.GraphedDiT(_Counted())
         inst(lat_d, t_d, ctx_d)
