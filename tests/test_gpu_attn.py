@@ -171,3 +171,24 @@ def test_attn_i8_key_split_merge(dev):
     assert float((out1.float() - out2.float()).abs().max()) <= 5e-2 * float(out1.float().abs().max())
     fp = torch.nn.functional.scaled_dot_product_attention(_heads(q, H), _heads(k, H), _heads(v, H))
     assert _cos(out2.cpu(), fp[0].permute(1, 0, 2).reshape(Lq, H * hd)) >= 0.999
+
+
+@pytest.mark.parametrize("mode", [10, 14])
+def test_attn_i8_two_warpgroups_per_tile_mode(dev, mode):
+    """Scheduling mode bit 3: two softmax warpgroups share a query row (64 keys of every block each, row max / row sum
+    combined through shared memory).  Same parity bars; output identical to the default mode up to the fp32 summation
+    order of the row sum."""
+    H, Lq, Lk, hd = 2, 520, 700, 128
+    g = torch.Generator().manual_seed(5)
+    q, k, v = (torch.randn(n, H * hd, generator=g) for n in (Lq, Lk, Lk))
+    ref, _ = _run(q, k, v, H, dev, debug=False)
+    b200q.load().b200q_attn_set_mode(mode)
+    try:
+        test_attn_i8_parity(dev, 2, 300, 333)
+        test_attn_i8_parity(dev, 12, 3400, 260)
+        test_attn_i8_parity(dev, 1, 5, 3)
+        out, _ = _run(q, k, v, H, dev, debug=False)
+    finally:
+        b200q.load().b200q_attn_set_mode(2)
+    if mode == 10:
+        assert float((out.float() - ref.float()).abs().max()) <= 1e-2 * float(ref.float().abs().max())

@@ -46,7 +46,15 @@ constexpr int BKEY = 128;          // keys per block
 constexpr int HD = 128;            // head dim == bytes per int8 row == one 128B swizzle row
 constexpr int TILE = 128 * 128;    // every operand tile is 16 KB
 constexpr int KS = 4, VS = 3, SCS = 4;
-constexpr int THREADS = 352;             // 11 warps: the register file then allows 186 registers per thread
+// NW = softmax warpgroups per Q tile.  NW = 1: one thread per query row handles all 128 keys of a block (352 threads).
+// NW = 2: two warpgroups share a row, 64 keys each (608 threads): four compute warps per scheduler instead of two, which
+// hides the fixed-latency dependency stalls the profile of the NW = 1 kernel shows (24 % of warp samples).
+template <int NW> struct Cfg {
+  static constexpr int compute_warps = 8 * NW;
+  static constexpr int threads = (compute_warps + 3) * 32;
+  static constexpr int cols = 128 / NW;           // key columns of a block per warpgroup
+  static constexpr int cw = 32 / NW;              // columns per tcgen05.ld / per inner chunk (4 chunks per block per WG)
+};
 constexpr uint32_t MAGIC_I = 0x4B400000u;    // bit pattern of 1.5*2^23: as_float(MAGIC_I + s) == 12582912 + s for |s| < 2^22
 constexpr float MAGIC_F = 12582912.0f;
 
@@ -56,7 +64,8 @@ struct Smem {
   static constexpr int v = k + KS * TILE;              // VS tiles
   static constexpr int p = v + VS * TILE;              // 2 tiles x 2 buffers
   static constexpr int sc = p + 4 * TILE;              // SCS x 128 x (c, d)
-  static constexpr int bar = sc + SCS * 1024;
+  static constexpr int xch = sc + SCS * 1024;          // row-statistics exchange between the warpgroups of a tile (NW = 2)
+  static constexpr int bar = xch + 2 * 2 * 2 * 128 * 4;
   static constexpr int total = bar + 512;
 };
 static_assert(Smem::total <= 232448, "dynamic smem budget (227 KB) exceeded");
@@ -113,8 +122,13 @@ __device__ __forceinline__ uint64_t exp2_poly2(float x0, float x1) {
   return pack_u32x2(q0 + (t0 << 23), q1 + (t1 << 23));          // (MAGIC_I + n) << 23 == n << 23 (mod 2^32)
 }
 
-template <bool PREMAGIC, bool POLY>
-__global__ void __launch_bounds__(THREADS, 1)
+template <int CW>
+__device__ __forceinline__ void tmem_ld_chunk(uint32_t taddr, uint32_t* v) {
+  if constexpr (CW == 32) tmem_ld_32x32(taddr, v); else tmem_ld_32x16(taddr, v);
+}
+
+template <bool PREMAGIC, bool POLY, int NW>
+__global__ void __launch_bounds__(Cfg<NW>::threads, 1)
 attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                const __grid_constant__ CUtensorMap tm_v, const Params p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -146,22 +160,24 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < SCS; ++i) { mbar_init(&sc_full[i], 1); mbar_init(&sc_empty[i], 8); }
+    for (int i = 0; i < SCS; ++i) { mbar_init(&sc_full[i], 1); mbar_init(&sc_empty[i], 8 * NW); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4);
-      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&s_free[i], 4 * NW);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4 * NW);
     }
-    for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 4); mbar_init(&p_free[i], 1); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&p_full[i], 4 * NW); mbar_init(&p_free[i], 1); }
     fence_barrier_init();
   }
-  if (warp == 8 && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
-  if (warp == 10) tmem_alloc<512>(tmem_slot);
+  constexpr int W_TMA = 8 * NW, W_MMA = 8 * NW + 1, W_SC = 8 * NW + 2;
+  constexpr int COLS = Cfg<NW>::cols, CW = Cfg<NW>::cw;
+  if (warp == W_TMA && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
+  if (warp == W_SC) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 8) {
+  if (warp == W_TMA) {
     // ===================== TMA producer =====================
     if (lane == 0) {
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
@@ -188,7 +204,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
       }
     }
-  } else if (warp == 9) {
+  } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
       constexpr uint32_t idesc_qk = idesc_i8(BQ, BKEY, true);
@@ -275,7 +291,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
       }
     }
-  } else if (warp == 10) {
+  } else if (warp == W_SC) {
     // ===================== per-key scale loader =====================
     int scs = 0; uint32_t scph = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
@@ -300,21 +316,24 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         }
       }
     }
-  } else if (warp < 8) {
+  } else if (warp < 8 * NW) {
     // ===================== softmax warpgroups =====================
-    const int t = warp >> 2, quarter = warp & 3;
+    const int t = warp / (4 * NW), half = (warp >> 2) % NW, quarter = warp & 3;
     const int r = quarter * 32 + lane;                                   // row inside the Q tile == TMEM lane
+    const int c0 = half * COLS;                                          // first key column (of a block) / O column of this WG
     const uint32_t t_lane = tmem_base + t * 256 + ((uint32_t)(quarter * 32) << 16);
     uint32_t useS = 0, pcnt = 0, itn = 0;
     int scs = 0; uint32_t scph = 0;
     constexpr uint32_t MG = PREMAGIC ? 0u : MAGIC_I;                      // int -> fp32 bias added here unless pre-initialised
     const uint64_t magic2 = pack_f32x2(MAGIC_F, MAGIC_F), c255 = pack_f32x2(255.f, 255.f);
+    float* xch_m = reinterpret_cast<float*>(smem + Smem::xch) + (t * 2) * 128;          // [half][row]
+    float* xch_l = reinterpret_cast<float*>(smem + Smem::xch) + 512 + (t * 2) * 128;
     auto release = [&](uint64_t* bar) {                                  // TMEM reads/writes of this warp done -> MMA issuer
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar);
     };
-    if (PREMAGIC) fill_magic(t_lane, 256);
+    if (PREMAGIC) { fill_magic(t_lane + c0, COLS); fill_magic(t_lane + 128 + c0, COLS); }
     release(&s_free[t]);
     release(&o_free[t]);
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
@@ -334,12 +353,12 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           const float4* s4 = reinterpret_cast<const float4*>(smem + Smem::sc + scs * 1024);
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch) {
-            uint32_t v[32];
-            tmem_ld_32x32(t_lane + hb * 128 + ch * 32, v);
+            uint32_t v[CW];
+            tmem_ld_chunk<CW>(t_lane + hb * 128 + c0 + ch * CW, v);
             tmem_ld_wait();
 #pragma unroll
-            for (int e = 0; e < 32; e += 2) {
-              const float4 cd = s4[(ch * 32 + e) >> 1];
+            for (int e = 0; e < CW; e += 2) {
+              const float4 cd = s4[(c0 + ch * CW + e) >> 1];
               const uint64_t t2 = fma_f32x2(pack_u32x2(v[e] + MG, v[e + 1] + MG), pack_f32x2(cd.x, cd.y), pack_f32x2(cd.z, cd.w));
               float t0, t1;
               unpack_f32x2(t2, t0, t1);
@@ -350,9 +369,14 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
           if (lane == 0) mbar_arrive(&sc_empty[scs]);
           if (++scs == SCS) { scs = 0; scph ^= 1; }
         }
-        if (PREMAGIC) fill_magic(t_lane, nblk * 128);
+        if (PREMAGIC) { fill_magic(t_lane + c0, COLS); if (nblk == 2) fill_magic(t_lane + 128 + c0, COLS); }
         release(&s_free[t]);
         ++useS;
+      }
+      if constexpr (NW == 2) {                                           // the two warpgroups of a tile saw 64 keys per block each
+        xch_m[half * 128 + r] = m;
+        named_bar_sync(1 + t, 256);
+        m = fmaxf(m, xch_m[(half ^ 1) * 128 + r]);
       }
 
       // ---- pass 2: P~ = exp2((S*dk - m)*a) -> u8 codes -> smem ; l = sum P~ ----
@@ -370,17 +394,17 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
         uint8_t* prow = smem + Smem::p + (t * 2 + pb) * TILE + r * 128;
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) {
-          uint32_t v[32];
-          tmem_ld_32x32(t_lane + ch * 32, v);
+          uint32_t v[CW];
+          tmem_ld_chunk<CW>(t_lane + c0 + ch * CW, v);
           tmem_ld_wait();
           if (ch == 3) {                                                 // S(j) is in registers: hand the columns back
-            if (PREMAGIC) fill_magic(t_lane, 128);
+            if (PREMAGIC) fill_magic(t_lane + c0, COLS);
             release(&s_free[t]);
           }
-          uint32_t w[8];
+          uint32_t w[CW / 4];
 #pragma unroll
-          for (int e = 0; e < 32; e += 4) {
-            const float4 cd0 = s4[(ch * 32 + e) >> 1], cd1 = s4[((ch * 32 + e) >> 1) + 1];
+          for (int e = 0; e < CW; e += 4) {
+            const float4 cd0 = s4[(c0 + ch * CW + e) >> 1], cd1 = s4[((c0 + ch * CW + e) >> 1) + 1];
             uint64_t t01 = fma_f32x2(pack_u32x2(v[e] + MG, v[e + 1] + MG), pack_f32x2(cd0.x, cd0.y), pack_f32x2(cd0.z, cd0.w));
             uint64_t t23 = fma_f32x2(pack_u32x2(v[e + 2] + MG, v[e + 3] + MG), pack_f32x2(cd1.x, cd1.y), pack_f32x2(cd1.z, cd1.w));
             t01 = fma_f32x2(t01, a2, nma2);
@@ -396,13 +420,16 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
             unpack_u32x2(fma_f32x2(p23, c255, magic2), u2, u3);
             w[e >> 2] = __byte_perm(__byte_perm(u0, u1, 0x0040), __byte_perm(u2, u3, 0x0040), 0x5410);
           }
-          // 32 consecutive keys of this row = two 16-byte chunks of the SWIZZLE_128B row
-          *reinterpret_cast<uint4*>(prow + (((ch * 2) ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
-          *reinterpret_cast<uint4*>(prow + (((ch * 2 + 1) ^ (r & 7)) << 4)) = make_uint4(w[4], w[5], w[6], w[7]);
+          // CW consecutive keys of this row = CW/16 16-byte chunks of the SWIZZLE_128B row
+          const int k16 = (c0 + ch * CW) >> 4;
+          *reinterpret_cast<uint4*>(prow + ((k16 ^ (r & 7)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+          if constexpr (CW == 32)
+            *reinterpret_cast<uint4*>(prow + (((k16 + 1) ^ (r & 7)) << 4)) = make_uint4(w[CW / 4 - 4], w[CW / 4 - 3], w[CW / 4 - 2], w[CW / 4 - 1]);
           if (p.p_out != nullptr && row_ok) {
-            uint8_t* g = p.p_out + ((long long)h * p.Lq + row) * p.ldp + j * BKEY + ch * 32;
+            uint8_t* g = p.p_out + ((long long)h * p.Lq + row) * p.ldp + j * BKEY + c0 + ch * CW;
             *reinterpret_cast<uint4*>(g) = make_uint4(w[0], w[1], w[2], w[3]);
-            *reinterpret_cast<uint4*>(g + 16) = make_uint4(w[4], w[5], w[6], w[7]);
+            if constexpr (CW == 32)
+              *reinterpret_cast<uint4*>(g + 16) = make_uint4(w[CW / 4 - 4], w[CW / 4 - 3], w[CW / 4 - 2], w[CW / 4 - 1]);
           }
         }
         fence_proxy_async_smem();                                        // generic-proxy writes -> visible to the tensor core
@@ -418,32 +445,40 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
       // ---- read-out: O = acc * dv[c] / (255 * l) ----
       float s0, s1;
       unpack_f32x2(sum2, s0, s1);
-      const float l = s0 + s1;
+      float l = s0 + s1;
+      if constexpr (NW == 2) {
+        xch_l[half * 128 + r] = l;
+        named_bar_sync(1 + t, 256);
+        l += xch_l[(half ^ 1) * 128 + r];
+      }
       const float inv = 1.0f / (255.0f * l);
       mbar_wait(&o_full[t], itn & 1);
       tcgen05_fence_after();
-      if (row_ok && p.m_out != nullptr) p.m_out[(long long)h * p.Lq + row] = m * a;
-      if (row_ok && p.l_out != nullptr) p.l_out[(long long)h * p.Lq + row] = l;
+      if (half == 0) {
+        if (row_ok && p.m_out != nullptr) p.m_out[(long long)h * p.Lq + row] = m * a;
+        if (row_ok && p.l_out != nullptr) p.l_out[(long long)h * p.Lq + row] = l;
+      }
       const float4* dv4 = reinterpret_cast<const float4*>(p.dv + h * HD);
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint32_t v[32];
-        tmem_ld_32x32(t_lane + 128 + ch * 32, v);
+        uint32_t v[CW];
+        tmem_ld_chunk<CW>(t_lane + 128 + c0 + ch * CW, v);
         tmem_ld_wait();
         if (ch == 3) {
-          if (PREMAGIC) fill_magic(t_lane + 128, 128);
+          if (PREMAGIC) fill_magic(t_lane + 128 + c0, COLS);
           release(&o_free[t]);
         }
         if (row_ok) {
+          const int col = c0 + ch * CW;
           if (p.acc_out != nullptr) {
-            int32_t* g = p.acc_out + (long long)row * p.ldacc + h * HD + ch * 32;
+            int32_t* g = p.acc_out + (long long)row * p.ldacc + h * HD + col;
 #pragma unroll
-            for (int e = 0; e < 32; e += 4) *reinterpret_cast<uint4*>(g + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
+            for (int e = 0; e < CW; e += 4) *reinterpret_cast<uint4*>(g + e) = make_uint4(v[e], v[e + 1], v[e + 2], v[e + 3]);
           }
-          __nv_bfloat16* g = p.out + (long long)row * p.ldo + h * HD + ch * 32;
+          __nv_bfloat16* g = p.out + (long long)row * p.ldo + h * HD + col;
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
-            const float4 d0 = __ldg(dv4 + ((ch * 32 + e) >> 2)), d1 = __ldg(dv4 + ((ch * 32 + e) >> 2) + 1);
+          for (int e = 0; e < CW; e += 8) {
+            const float4 d0 = __ldg(dv4 + ((col + e) >> 2)), d1 = __ldg(dv4 + ((col + e) >> 2) + 1);
             __nv_bfloat162 o0 = __floats2bfloat162_rn((float)(int)v[e] * (d0.x * inv), (float)(int)v[e + 1] * (d0.y * inv));
             __nv_bfloat162 o1 = __floats2bfloat162_rn((float)(int)v[e + 2] * (d0.z * inv), (float)(int)v[e + 3] * (d0.w * inv));
             __nv_bfloat162 o2 = __floats2bfloat162_rn((float)(int)v[e + 4] * (d1.x * inv), (float)(int)v[e + 5] * (d1.y * inv));
@@ -461,7 +496,7 @@ attn_i8_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  if (warp == 10) tmem_dealloc<512>(tmem_base);
+  if (warp == W_SC) tmem_dealloc<512>(tmem_base);
 }
 
 // ---- V^T quantizer: per-(head, channel) scale over all tokens, codes written transposed ---------------------------------
@@ -568,10 +603,11 @@ extern "C" int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C,
 
 // scheduling knob (b200q_attn_set_mode): bit 0 = S accumulators pre-initialised with the int->fp32 bias (tcgen05.st),
 // bit 1 = pass 1 hands two key blocks per barrier round trip, bit 2 = a quarter of the exponentials of pass 2 evaluated by
-// a polynomial on the FMA/ALU pipes instead of the MUFU.  Bits 0-1: results identical; bit 2: P~ within 7e-6 relative.
+// a polynomial on the FMA/ALU pipes instead of the MUFU, bit 3 = two softmax warpgroups per Q tile (64 keys of a block
+// each, 608 threads).  Bits 0, 1, 3: results identical (bit 3 up to the fp32 summation order of l); bit 2: P~ within 7e-6.
 static int g_attn_mode = 2;   // measured on B200 (tools/probe_attn_i8.py, H=12 L=32760): mode 0 7.99 ms, 1 8.77, 2 7.57, 3 8.55
 extern "C" int b200q_attn_set_mode(int mode) {
-  if (mode < 0 || mode > 7) return B200Q_ERR_BAD_ARG;
+  if (mode < 0 || mode > 15) return B200Q_ERR_BAD_ARG;
   g_attn_mode = mode;
   return B200Q_OK;
 }
@@ -621,21 +657,28 @@ extern "C" int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int
 
   static bool configured = false;
   if (!configured) {
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+#define B200Q_ATTN_CFG(A, B, C) \
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_i8_kernel<A, B, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total))
+    B200Q_ATTN_CFG(false, false, 1); B200Q_ATTN_CFG(true, false, 1); B200Q_ATTN_CFG(false, true, 1); B200Q_ATTN_CFG(true, true, 1);
+    B200Q_ATTN_CFG(false, false, 2); B200Q_ATTN_CFG(true, false, 2); B200Q_ATTN_CFG(false, true, 2); B200Q_ATTN_CFG(true, true, 2);
+#undef B200Q_ATTN_CFG
     configured = true;
   }
   p.p1_two = (g_attn_mode & 2) ? 1 : 0;
   int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   cudaStream_t st = (cudaStream_t)stream;
-  switch (g_attn_mode & 5) {
-    case 0: attn_i8_kernel<false, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 1: attn_i8_kernel<true, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 4: attn_i8_kernel<false, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    default: attn_i8_kernel<true, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+#define B200Q_ATTN_LAUNCH(A, B, C) attn_i8_kernel<A, B, C><<<grid, Cfg<C>::threads, Smem::total, st>>>(tq, tk, tv, p)
+  switch (g_attn_mode & 13) {
+    case 0: B200Q_ATTN_LAUNCH(false, false, 1); break;
+    case 1: B200Q_ATTN_LAUNCH(true, false, 1); break;
+    case 4: B200Q_ATTN_LAUNCH(false, true, 1); break;
+    case 5: B200Q_ATTN_LAUNCH(true, true, 1); break;
+    case 8: B200Q_ATTN_LAUNCH(false, false, 2); break;
+    case 9: B200Q_ATTN_LAUNCH(true, false, 2); break;
+    case 12: B200Q_ATTN_LAUNCH(false, true, 2); break;
+    default: B200Q_ATTN_LAUNCH(true, true, 2); break;
   }
+#undef B200Q_ATTN_LAUNCH
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
