@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--ffn-bits", type=int, default=8, choices=[4, 8], help="4 = W4A8 FFN weights (configs[4])")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra int8-attention timing at N=1")
     ap.add_argument("--max-seconds", type=float, default=600.0, help="watchdog: hard-exit after this wall-clock time")
+    ap.add_argument("--pipeline-chunks", type=int, default=1,
+                    help="N>1: exchange/attend the heads of a rank's head group in this many chunks (exchange overlaps attention)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 
@@ -234,7 +236,7 @@ def run_b200(args):
     if args.model == "14B":
         LATENT_SHAPE = (16, 21, 90, 160)                        # 1280x720x81 -> 75,600 tokens (BASELINE configs[3])
     default_cfg = args.model == "1.3B" and args.attn == "bf16" and args.ffn_bits == 8
-    sp = SequenceParallel() if world > 1 else None
+    sp = SequenceParallel(pipeline_chunks=args.pipeline_chunks) if world > 1 else None
     dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers, attn_quant=(args.attn == "int8"),
                            ffn_bits=args.ffn_bits)
     L = (LATENT_SHAPE[1] // 1) * (LATENT_SHAPE[2] // 2) * (LATENT_SHAPE[3] // 2)
@@ -469,6 +471,7 @@ def run_b200(args):
             b, pu, pr = exchange_bytes_per_rank(L, cfg.dim, world, cfg.num_heads)
             out["config"]["exchange_bytes_per_rank_per_block"] = b
             out["config"]["head_plan"] = f"Pu={pu} x Pr={pr}"
+            out["config"]["pipeline_chunks"] = args.pipeline_chunks
         if args.layers is not None and args.layers != cfg.num_layers:
             out["invalid"] = f"debug run with {args.layers} of {cfg.num_layers} blocks"
         if world == 1 and not args.no_cpu_baseline:

@@ -26,7 +26,7 @@ def _cpu_attention(q, k, v, heads):
     return o.squeeze(0).permute(1, 0, 2).reshape(Lq, heads * hd)
 
 
-def _worker(rank, world, port, heads, L, hd, out_q):
+def _worker(rank, world, port, heads, L, hd, out_q, chunks=1):
     sys.path.insert(0, os.path.join(ROOT, "wan2.1-quantization_b200"))
     sys.path.insert(0, ROOT)
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
@@ -36,10 +36,13 @@ def _worker(rank, world, port, heads, L, hd, out_q):
     D = heads * hd
     q, k, v = (torch.randn(L, D) for _ in range(3))
     full = _cpu_attention(q, k, v, heads)
-    sp = SequenceParallel(attention_core=_cpu_attention)
+    sp = SequenceParallel(attention_core=_cpu_attention, pipeline_chunks=chunks)
     (qs, off, Lr), (ks, _, _), (vs, _, _) = sp.shard_tokens(q), sp.shard_tokens(k), sp.shard_tokens(v)
     o = sp.attention(qs.contiguous(), ks.contiguous(), vs.contiguous(), heads)
     ok_attn = torch.allclose(o, full[off:off + Lr], rtol=1e-5, atol=1e-6)
+    if chunks > 1:       # the head-chunked pipeline is the same permutation: bit-identical to the single exchange
+        sp1 = SequenceParallel(attention_core=_cpu_attention)
+        ok_attn = ok_attn and torch.equal(o, sp1.attention(qs.contiguous(), ks.contiguous(), vs.contiguous(), heads))
     gathered = sp.gather_tokens(o, L)
     ok_gather = torch.allclose(gathered, full, rtol=1e-5, atol=1e-6)
     # calibration: sharded rows + allreduce(MAX) == unsharded abs-max, bit for bit
@@ -57,6 +60,23 @@ def test_sequence_parallel_attention_gloo(world, heads):
     out_q = ctx.Queue()
     port = _free_port()
     procs = [ctx.Process(target=_worker, args=(r, world, port, heads, 48, 8, out_q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [out_q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, ok_attn, ok_gather, ok_cal, plan in res:
+        assert ok_attn and ok_gather and ok_cal, (rank, ok_attn, ok_gather, ok_cal, plan)
+
+
+@pytest.mark.parametrize("world,heads,chunks", [(2, 12, 3), (4, 12, 3), (4, 8, 2)])
+def test_pipelined_exchange_gloo(world, heads, chunks):
+    """pipeline_chunks > 1 (exchange of head chunk c+1 overlapping the attention of chunk c) gives the same result."""
+    ctx = mp.get_context("spawn")
+    out_q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, heads, 48, 8, out_q, chunks)) for r in range(world)]
     for p in procs:
         p.start()
     res = [out_q.get(timeout=120) for _ in range(world)]

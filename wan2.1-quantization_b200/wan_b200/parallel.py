@@ -33,7 +33,12 @@ def _largest_head_divisor(world, heads):
 
 
 class SequenceParallel:
-    def __init__(self, group=None, attention_core=None):
+    def __init__(self, group=None, attention_core=None, pipeline_chunks=1):
+        """pipeline_chunks > 1: the heads of a rank's head group are exchanged and attended in that many chunks, so the
+        NCCL transfer of chunk c+1 (and the return of chunk c-1) runs while the attention core works on chunk c
+        (send/recv are asynchronous on NCCL's stream; only the consumer waits).  Results are bit-identical to the
+        single-exchange path - attention is independent per head."""
+        self.pipeline_chunks = int(pipeline_chunks)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -85,6 +90,22 @@ class SequenceParallel:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
 
+    def _exchange_async(self, sends, recvs):
+        """like _exchange, but returns the outstanding work handles instead of waiting on them"""
+        ops = []
+        for peer in range(self.world_size):
+            s, r = sends[peer], recvs[peer]
+            if peer == self.rank:
+                if r is not None and s is not None:
+                    r.copy_(s)
+                continue
+            if r is not None and r.numel() > 0:
+                ops.append(dist.P2POp(dist.irecv, r, self._global(peer), group=self.group))
+            if s is not None and s.numel() > 0:
+                ops.append(dist.P2POp(dist.isend, s, self._global(peer), group=self.group))
+                self.bytes_sent += s.numel() * s.element_size()
+        return dist.batch_isend_irecv(ops) if ops else []
+
     def _global(self, peer):
         return peer if self.group is None else dist.get_global_rank(self.group, peer)
 
@@ -100,6 +121,9 @@ class SequenceParallel:
         Pu, Pr, g, h = self.plan(num_heads)
         Hg = num_heads // Pu
         W = Hg * hd
+        C = self.pipeline_chunks
+        if C > 1 and Hg % C == 0:
+            return self._attention_pipelined(q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C)
         # pack per destination: [k | v | (q)] for the destination's head group
         sends, recvs = [None] * P, [None] * P
         for dst in range(P):
@@ -126,6 +150,50 @@ class SequenceParallel:
             recvs[h * Pu + gsrc] = torch.empty((Lr, W), dtype=q.dtype, device=q.device)
         self._exchange(sends, recvs)
         return torch.cat([recvs[h * Pu + gsrc] for gsrc in range(Pu)], 1)        # [Lr, H*hd]
+
+    def _attention_pipelined(self, q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C):
+        """Head-chunked variant of attention(): chunk c of every head group travels as its own grouped send/recv; all
+        inbound exchanges are posted up front, each chunk's attention waits only for its own operands, and its output
+        is sent back while the next chunk is being computed."""
+        P = self.world_size
+        Hc = Hg // C
+        Wc, W = Hc * hd, Hg * hd
+        q_src = [s for s in range(P) if s // Pu == h]
+        inbound = []
+        for c in range(C):
+            sends, recvs = [None] * P, [None] * P
+            for dst in range(P):
+                gd, hdst = dst % Pu, dst // Pu
+                cols = slice(gd * W + c * Wc, gd * W + (c + 1) * Wc)
+                parts = [k[:, cols], v[:, cols]]
+                if hdst == h:
+                    parts.append(q[:, cols])
+                sends[dst] = torch.stack(parts, 0).contiguous()
+            for src in range(P):
+                n = 3 if (src // Pu) == h else 2
+                recvs[src] = torch.empty((n, Lr, Wc), dtype=q.dtype, device=q.device)
+            inbound.append((self._exchange_async(sends, recvs), recvs, sends))
+        outbound, out_recvs = [], []
+        for c in range(C):
+            works, recvs, _keep = inbound[c]
+            for w in works:
+                w.wait()
+            K = torch.cat([recvs[s][0] for s in range(P)], 0)
+            V = torch.cat([recvs[s][1] for s in range(P)], 0)
+            Q = torch.cat([recvs[s][2] for s in q_src], 0)
+            O = core(Q, K, V, Hc)                                                  # [L/Pr, Wc]
+            sends, recvs_o = [None] * P, [None] * P
+            for i, s in enumerate(q_src):
+                sends[s] = O[i * Lr:(i + 1) * Lr].contiguous()
+            for gsrc in range(Pu):
+                recvs_o[h * Pu + gsrc] = torch.empty((Lr, Wc), dtype=q.dtype, device=q.device)
+            outbound.append((self._exchange_async(sends, recvs_o), sends))
+            out_recvs.append(recvs_o)
+        for works, _keep in outbound:
+            for w in works:
+                w.wait()
+        # column order of the result: head group gsrc, then chunk c inside the group
+        return torch.cat([out_recvs[c][h * Pu + gsrc] for gsrc in range(Pu) for c in range(C)], 1)
 
     # ---- calibration ---------------------------------------------------------------------------------------------
     def allreduce_max(self, flat_stats):
