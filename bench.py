@@ -50,8 +50,9 @@ def parse():
     ap.add_argument("--ffn-bits", type=int, default=8, choices=[4, 8], help="4 = W4A8 FFN weights (configs[4])")
     ap.add_argument("--no-variants", action="store_true", help="skip the extra int8-attention timing at N=1")
     ap.add_argument("--max-seconds", type=float, default=600.0, help="watchdog: hard-exit after this wall-clock time")
-    ap.add_argument("--pipeline-chunks", type=int, default=1,
-                    help="N>1: exchange/attend the heads of a rank's head group in this many chunks (exchange overlaps attention)")
+    ap.add_argument("--pipeline-chunks", type=int, default=0,
+                    help="N>1: exchange/attend the heads of a rank's head group in this many chunks (exchange overlaps attention); "
+                         "0 = auto: 3 at N=2 (measured 128.1 -> 120.7 ms on 2 B200), 1 elsewhere (not yet measured at N=4/8)")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying the CUDA graph")
     return ap.parse_args()
 
@@ -236,6 +237,8 @@ def run_b200(args):
     if args.model == "14B":
         LATENT_SHAPE = (16, 21, 90, 160)                        # 1280x720x81 -> 75,600 tokens (BASELINE configs[3])
     default_cfg = args.model == "1.3B" and args.attn == "bf16" and args.ffn_bits == 8
+    if args.pipeline_chunks == 0:
+        args.pipeline_chunks = 3 if (world == 2 and (cfg.num_heads // 2) % 3 == 0) else 1
     sp = SequenceParallel(pipeline_chunks=args.pipeline_chunks) if world > 1 else None
     dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers, attn_quant=(args.attn == "int8"),
                            ffn_bits=args.ffn_bits)

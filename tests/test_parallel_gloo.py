@@ -70,7 +70,7 @@ def test_sequence_parallel_attention_gloo(world, heads):
         assert ok_attn and ok_gather and ok_cal, (rank, ok_attn, ok_gather, ok_cal, plan)
 
 
-@pytest.mark.parametrize("world,heads,chunks", [(2, 12, 3), (4, 12, 3), (4, 8, 2)])
+@pytest.mark.parametrize("world,heads,chunks", [(2, 12, 3), (4, 12, 3), (4, 8, 2), (4, 6, 3)])
 def test_pipelined_exchange_gloo(world, heads, chunks):
     """pipeline_chunks > 1 (exchange of head chunk c+1 overlapping the attention of chunk c) gives the same result."""
     ctx = mp.get_context("spawn")
