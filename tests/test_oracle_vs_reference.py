@@ -51,6 +51,28 @@ for (cin, cout, wb) in [(1536, 256, 8), (320, 192, 4), (8960, 64, 8)]:
         y = layer(x.clone())
     assert torch.equal(y, O.quantized_linear_fake(x, w0, fp.bias.detach(), w_bits=wb))
     n += 1
+# attention: q/k/v DynamicQuantizers with the reshapes of quant_opensora.py:430-442, map quantizers of both groupings
+qa = ref["quant_attn"]
+for (H, Lq, Lk, hd) in [(2, 24, 40, 128), (3, 17, 9, 64), (2, 32, 32, 64)]:
+    q = torch.randn(1, H, Lq, hd, generator=g) * 2; k = torch.randn(1, H, Lk, hd, generator=g); v = torch.randn(1, H, Lk, hd, generator=g)
+    cfg = OmegaConf.create({"n_bits": 8, "sym": True})
+    zq, zk, zv, zp = (bq.DynamicQuantizer(cfg) for _ in range(4))
+    for z in (zq, zk, zv, zp): z.module_name = "t"
+    qd = zq(q.reshape([-1, hd])).reshape([1, H, Lq, hd]); kd = zk(k.reshape([-1, hd])).reshape([1, H, Lk, hd])
+    vd = zv(v.permute([0, 1, 3, 2]).reshape([-1, Lk])).reshape([1, H, hd, Lk]).permute([0, 1, 3, 2])
+    attn = ((qd * hd ** -0.5) @ kd.transpose(-2, -1)).to(torch.float32).softmax(dim=-1)
+    pmax = attn.max(dim=-1, keepdim=True)[0].expand_as(attn).clone()
+    out_ref = zp.forward_with_quant_params(attn.clone(), pmax.clone()) @ vd
+    out, info = O.quantized_attention_rowstep(q, k, v)
+    assert torch.equal(out, out_ref) and torch.equal(info["dv"].flatten(), zv.delta.flatten())
+    if Lq == Lk:          # the reference's 'row' grouping reshapes the map as [B, H, N, N] (quant_attn.py:169-173)
+        acfg = OmegaConf.create({"attn": {"qk": {"n_bits": 8, "sym": True, "reorder_file_path": None},
+                                          "attn_map": {"n_bits": 8, "sym": False, "group": "row"}}})
+        pm = qa.QuantizedAttentionMapOpenSORA(acfg); pm.attn_map_quantizer.module_name = "t"
+        out_ref2 = pm(attn.clone()) @ vd
+        out2, _ = O.quantized_attention_fake(q, k, v, p_sym=False)
+        assert torch.equal(out2, out_ref2)
+    n += 1
 print("ORACLE_PINNED", n)
 '''
 
