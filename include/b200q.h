@@ -237,7 +237,8 @@ B200Q_API int b200q_attn_i8(const int8_t* qq, int64_t ldq, const float* dq, int6
 /* Scheduling knob of b200q_attn_i8 (debug / benchmarking; results identical): bit 0 = S accumulators pre-initialised
  * with the int->fp32 conversion bias by tcgen05.st, bit 1 = pass 1 hands two key blocks per barrier round trip,
  * bit 2 = a quarter of the softmax exponentials evaluated by a degree-4 polynomial on the FMA/ALU pipes instead of the
- * MUFU (P~ within 7e-6 relative of the MUFU path; bits 0-1 leave results bit-identical). */
+ * MUFU (P~ within 7e-6 relative of the MUFU path), bit 3 = two softmax warpgroups per query tile (608 threads).
+ * Bits 0, 1, 3 leave codes and accumulators bit-identical.  Default 2; measurements in DESIGN.md section 4c. */
 B200Q_API int b200q_attn_set_mode(int mode);
 
 #ifdef __cplusplus
