@@ -450,16 +450,15 @@ class GraphedDiT:
         return out
 
     def _capture(self, key, latent, t, context):
-        if True:
-            lat_s, t_s, ctx_s = latent.clone(), t.clone(), context.clone()
-            side = torch.cuda.Stream()
-            side.wait_stream(torch.cuda.current_stream())
-            with torch.cuda.stream(side):                       # warm-up off the default stream (allocator, rope tables, NCCL)
-                for _ in range(self.warmup):
-                    self.dit.forward(lat_s, t_s, ctx_s)
-            torch.cuda.current_stream().wait_stream(side)
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                out = self.dit.forward(lat_s, t_s, ctx_s)
-            self.graphs[key] = (g, lat_s, t_s, ctx_s, out)
+        lat_s, t_s, ctx_s = latent.clone(), t.clone(), context.clone()
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                           # warm-up off the default stream (allocator, rope tables, NCCL)
+            for _ in range(self.warmup):
+                self.dit.forward(lat_s, t_s, ctx_s)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = self.dit.forward(lat_s, t_s, ctx_s)
+        self.graphs[key] = (g, lat_s, t_s, ctx_s, out)
