@@ -118,23 +118,24 @@ def get_hadK(n, transpose=False):
 
 
 def matmul_hadU(X, transpose=False):
-    """X @ (H_n / sqrt(n)) along the last dim, H_n = H_{2^m} (x) ... butterflies then the order-K base block, the
-    factorisation of quarot_utils.py:158-179 (butterfly stages down to K rows, then hadK @)."""
+    """X @ (H_n / sqrt(n)) along the last dim with H_n = H_K (x) H_{2^m} (index = a*2^m + b): a natural-order fast
+    Walsh-Hadamard transform over the low m index bits, then the order-K base block over the K segments.  Same operator
+    as the reference's matmul_hadU (quarot_utils.py:158-179: butterfly stages down to K rows, then hadK @)."""
     n = X.shape[-1]
-    hadK, K = get_hadK(n, transpose)
-    inp = X.clone().reshape(-1, n, 1)
-    out = inp.clone()
-    while inp.shape[1] > K:
-        inp = inp.view(inp.shape[0], inp.shape[1] // 2, 2, inp.shape[2])
-        out = out.view(inp.shape)
-        out[:, :, 0, :] = inp[:, :, 0, :] + inp[:, :, 1, :]
-        out[:, :, 1, :] = inp[:, :, 0, :] - inp[:, :, 1, :]
-        out = out.view(inp.shape[0], inp.shape[1], -1)
-        inp, out = out, inp
-    del out
+    K, m = hadamard_factor(n)
+    width = 1 << m
+    y = X.reshape(-1, K, width).clone()
+    h = 1
+    while h < width:
+        y = y.view(-1, K, width // (2 * h), 2, h)
+        lo, hi = y[..., 0, :], y[..., 1, :]
+        y = torch.stack((lo + hi, lo - hi), dim=-2)
+        h *= 2
+    y = y.reshape(-1, K, width)
     if K > 1:
-        inp = hadK.view(1, K, K).to(inp) @ inp
-    return inp.reshape(X.shape) / math.sqrt(n)
+        HK = base_hadamard(K).to(y)
+        y = torch.einsum("ij,bjk->bik", HK.t() if transpose else HK, y)
+    return y.reshape(X.shape) / math.sqrt(n)
 
 
 def matmul_hadUt(X):
