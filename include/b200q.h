@@ -199,6 +199,22 @@ B200Q_API int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows,
                              void* out, int64_t ldo, int8_t* q_out, int64_t ldq, float* dq_out, int n_bits,
                              b200q_stream_t stream);
 
+/* ---- (f-2) smooth scale + randomized Hadamard rotation fused into the per-token quantizer ----
+ * y = (x * colscale) . (H_K (x) H_{2^log2_width});  q = rne(y/delta), delta = max|y| / n_levels (floor 1e-6): the
+ * activation side of ViDiTQuantizedLinear / QuarotQuantizedLinear / SQQuantizedLinear.forward
+ * (quant_utils/qdiff/viditq/viditq_quant_layer.py:58-66, quarot/quarot_quant_layer.py:55-62,
+ * smooth_quant/sq_quant_layer.py:55-58), where the reference multiplies by the channel mask and then by a dense fp64
+ * [n, n] rotation matrix.  A rotation R = diag(s) . H_n / sqrt(n) (random_hadamard_matrix, quarot/quarot_utils.py:186-192)
+ * is passed in factored form: colscale[c] = channel_mask[c] * s[c] / sqrt(n) (fp32 [cols], NULL = ones), hadK = the
+ * order-K base block (+-1 entries, fp32 [K*K] row-major, out[i] = sum_j hadK[i][j] * segment_j; NULL iff K == 1),
+ * cols == K << log2_width with log2_width in [5, 8]; log2_width == 0 and K == 1 applies colscale only (SmoothQuant).
+ * Same operator as matmul_hadU (quarot_utils.py:158-179) evaluated in fp32.  cols % 128 == 0, K <= 32.
+ * rowsum (int32 [rows]) and y_out (fp32 [rows, cols], the rotated activations) are optional. */
+B200Q_API int b200q_had_quant_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                         const float* colscale, const float* hadK, int K, int log2_width, int n_bits,
+                         int8_t* q, int64_t ldq, float* delta, int32_t* rowsum, float* y_out, int64_t ldy,
+                         b200q_stream_t stream);
+
 /* ---- (c) quantized attention ------------------------------------------------------------
  * Replaces the reference's materialised fake-quant attention (examples/Wan2.1/models/quant_opensora.py:430-478:
  * q/k/v DynamicQuantizers, `q*scale @ k^T`, fp32 softmax, attention-map quantizer, `attn @ v`), which builds

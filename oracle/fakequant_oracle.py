@@ -352,3 +352,72 @@ def make_block_params(dim, ffn_dim, seed=0, bias_std=0.02):
     p["ffn.2.bias"] = torch.randn(dim, generator=g) * bias_std
     p["modulation"] = torch.randn(1, 6, dim, generator=g) / dim ** 0.5
     return p
+
+
+# --------------------------------------------------------------------------
+# full DiT step
+# --------------------------------------------------------------------------
+def sinusoidal_embedding_1d(dim, position):
+    """model.py:17-28 (float64)"""
+    half = dim // 2
+    position = position.type(torch.float64)
+    sinusoid = torch.outer(position, torch.pow(10000, -torch.arange(half).to(position).div(half)))
+    return torch.cat([torch.cos(sinusoid), torch.sin(sinusoid)], dim=1)
+
+
+class WanDiTOracle:
+    """WanModel.forward (wan/modules/model.py:539-631) for ONE sample, fp32 on CPU, restated over a state dict with
+    WanModel's parameter names: patch embedding (Conv3d with stride == kernel, :508-509), sinusoidal time embedding ->
+    time_embedding -> time_projection (:585-590), text_embedding on the zero-padded context (:593-599), the blocks
+    (WanBlockOracle), Head (:388-401: LayerNorm, modulation, linear) and unpatchify (:633-656).
+    `lin(name, x, default)` (optional) overrides individual block linears, name = 'blocks.<i>.<layer>' — used by the
+    tests to model layers the quant config keeps FP or runs as SmoothQuant / QuaRot / ViDiT-Q variants."""
+
+    def __init__(self, sd, dim, ffn_dim, num_heads, num_layers, freq_dim=256, text_len=512, patch_size=(1, 2, 2),
+                 out_dim=16, eps=1e-6, lin=None, **block_kw):
+        self.sd = {k: v.detach().float().cpu() for k, v in sd.items() if torch.is_tensor(v)}
+        self.dim, self.freq_dim, self.text_len, self.patch_size, self.out_dim, self.eps = dim, freq_dim, text_len, patch_size, out_dim, eps
+        self.blocks = []
+        for i in range(num_layers):
+            pre = f"blocks.{i}."
+            p = {k[len(pre):]: v for k, v in self.sd.items() if k.startswith(pre)}
+            blk = WanBlockOracle(p, dim, ffn_dim, num_heads, eps=eps, **block_kw)
+            if lin is not None:
+                default = blk.lin
+                blk.lin = (lambda name, x, _pre=pre, _d=default: lin(_pre + name, x, lambda: _d(name, x)))
+            self.blocks.append(blk)
+
+    def embed(self, latent, t, context):
+        """-> x [L, D], e [1, D], e0 [6, D], ctx [text_len, D], grid"""
+        sd = self.sd
+        x = F.conv3d(latent.float().unsqueeze(0), sd["patch_embedding.weight"], sd["patch_embedding.bias"], stride=self.patch_size)
+        grid = tuple(x.shape[2:])
+        x = x.flatten(2).transpose(1, 2)[0]
+        te = sinusoidal_embedding_1d(self.freq_dim, t.reshape(-1)[:1]).float()
+        e = F.linear(F.silu(F.linear(te, sd["time_embedding.0.weight"], sd["time_embedding.0.bias"])),
+                     sd["time_embedding.2.weight"], sd["time_embedding.2.bias"])
+        e0 = F.linear(F.silu(e), sd["time_projection.1.weight"], sd["time_projection.1.bias"]).view(6, self.dim)
+        ctx = torch.zeros(self.text_len, context.shape[1])
+        ctx[:context.shape[0]] = context.float()
+        ctx = F.linear(F.gelu(F.linear(ctx, sd["text_embedding.0.weight"], sd["text_embedding.0.bias"]), approximate="tanh"),
+                       sd["text_embedding.2.weight"], sd["text_embedding.2.bias"])
+        return x, e, e0, ctx, grid
+
+    def head(self, x, e):
+        """Head.forward, model.py:388-401"""
+        sd = self.sd
+        m = (sd["head.modulation"].reshape(2, -1) + e).unbind(0)
+        return F.linear(layer_norm(x, None, None, self.eps) * (1 + m[1]) + m[0], sd["head.head.weight"], sd["head.head.bias"])
+
+    def unpatchify(self, y, grid):
+        """model.py:633-656"""
+        c = self.out_dim
+        u = y.view(*grid, *self.patch_size, c)
+        u = torch.einsum("fhwpqrc->cfphqwr", u)
+        return u.reshape(c, *[i * j for i, j in zip(grid, self.patch_size)])
+
+    def forward(self, latent, t, context):
+        x, e, e0, ctx, grid = self.embed(latent, t, context)
+        for blk in self.blocks:
+            x = blk.forward(x, e0, grid, ctx)
+        return self.unpatchify(self.head(x, e), grid)

@@ -52,9 +52,35 @@ def gemm_w4a8(qa, qw4, K, *args, **kwargs):
     return gemm_w8a8(qa, qw4, *args, **kwargs)
 
 
+def had_transform(x, colscale=None, hadK=None, K=1, log2_width=0):
+    """float64 restatement of what b200q_had_quant_rows applies in front of its quantizer (include/b200q.h)."""
+    y = x.double()
+    if colscale is not None:
+        y = y * colscale.double().reshape(1, -1)
+    if log2_width > 0:
+        W = 1 << log2_width
+        y = y.reshape(-1, K, W)
+        h = 1
+        while h < W:
+            y = y.reshape(-1, K, W // (2 * h), 2, h)
+            y = torch.stack((y[..., 0, :] + y[..., 1, :], y[..., 0, :] - y[..., 1, :]), dim=-2)
+            h *= 2
+        y = y.reshape(-1, K, W)
+        if K > 1:
+            y = torch.einsum("ij,bjk->bik", hadK.double().reshape(K, K), y)
+        y = y.reshape(x.shape)
+    return y
+
+
+def had_quant_rows(x, colscale=None, hadK=None, K=1, log2_width=0, n_bits=8, want_rowsum=True, want_y=False, out=None):
+    y = had_transform(x, colscale, hadK, K, log2_width).float()
+    q, d, _, rs = quant_rows(y, n_bits, True, True, want_rowsum)
+    return q, d, rs, (y if want_y else None)
+
+
 def install(monkeypatch):
     import b200q
     import qdiff.base.base_quantizer as bq
-    for name in ("quant_rows", "quant_rows_static", "dequant_rows", "gemm_w8a8", "pack_w4", "gemm_w4a8"):
+    for name in ("quant_rows", "quant_rows_static", "dequant_rows", "gemm_w8a8", "pack_w4", "gemm_w4a8", "had_quant_rows"):
         monkeypatch.setattr(b200q, name, globals()[name])
     monkeypatch.setattr(bq, "_on_cuda", lambda x: (x, None))

@@ -17,7 +17,9 @@ def _codes(rows, cols, seed, lo=-127, hi=127):
 
 
 SHAPES = [(128, 256, 128), (256, 512, 256), (384, 256, 1536), (130, 272, 144), (1, 8, 16), (515, 1536, 1536),
-          (100, 100, 4096), (128, 8960, 320), (777, 300, 208)]
+          (100, 100, 4096), (128, 8960, 320), (777, 300, 208),
+          # the Wan-14B GEMM dims of SURVEY §8d (reduced M): K = 13824 (ffn.2), N = 13824 (ffn.0), N = K = 5120
+          (200, 5120, 13824), (150, 13824, 5120), (260, 5120, 5120), (140, 15360, 5120), (200, 1536, 8960)]
 
 
 @pytest.mark.parametrize("M,N,K", SHAPES)

@@ -198,3 +198,57 @@ def test_gate_residual(dev, ydt, rows, cols):
     assert torch.equal(out.cpu(), res + y.float() * gate)
     out = b200q.gate_residual(y.to(dev), res.clone().to(dev), None)
     assert torch.equal(out.cpu(), res + y.float())
+
+
+def test_mixed_precision_quantizers_golden_gpu(dev, golden_dir):
+    """MixedPrecisionStaticQuantizer / MixedPrecisionDynamicQuantizer of the mirror on libb200q vs the outputs of the
+    imported reference classes (mixed_precision_quantizer.py:56-186; golden/mixed_precision.pt): delta / zero_point lists,
+    the selected entry, the dequantised tensor before and after bitwidth_refactor - all bit-exact."""
+    import os
+    from omegaconf import OmegaConf
+    from qdiff.base.mixed_precision_quantizer import MixedPrecisionDynamicQuantizer, MixedPrecisionStaticQuantizer
+    rec = torch.load(os.path.join(golden_dir, "mixed_precision.pt"))
+    w = rec["w"].to(dev)
+    for i in (0, 1):
+        qz = MixedPrecisionStaticQuantizer(OmegaConf.create({"n_bits": [4, 8], "sym": False, "i_bitwidth": i}))
+        deq = qz.forward(w.clone())
+        g = rec[f"static_i{i}"]
+        assert torch.equal(qz.delta.cpu(), g["delta"]) and torch.equal(qz.zero_point.cpu(), g["zero_point"])
+        assert torch.equal(qz.delta_list.cpu(), g["delta_list"]) and torch.equal(qz.zero_point_list.cpu(), g["zero_point_list"])
+        assert torch.equal(deq.cpu(), g["dequant"])
+        qz.init_done = True
+        qz.bitwidth_refactor(1 - i)
+        gr = rec[f"static_i{i}_refactored"]
+        assert torch.equal(qz.delta.cpu(), gr["delta"]) and torch.equal(qz.forward(w.clone()).cpu(), gr["dequant"])
+        assert qz.n_bits == (8, 4)[i]
+        gd = rec[f"dynamic_i{i}"]
+        dz = MixedPrecisionDynamicQuantizer(OmegaConf.create({"n_bits": [4, 8], "sym": True, "i_bitwidth": i}))
+        assert torch.equal(dz.forward(gd["x"].to(dev)).cpu(), gd["dequant"]) and torch.equal(dz.delta.cpu(), gd["delta"])
+        # the real-integer entry the quantized linear uses gives the same codes
+        q, d, _, rs = dz.quantize_int8(gd["x"].to(dev))
+        assert torch.equal((q.float() * d.unsqueeze(1)).cpu(), gd["dequant"]) and torch.equal(rs.cpu(), q.cpu().to(torch.int32).sum(1).to(torch.int32))
+
+
+def test_static_quantizer_running_statistics_and_fp32_params_gpu(dev):
+    """base_quantizer.py:76-88: x_max / x_min are running statistics over init_quant_params calls while delta follows the
+    current rows; 16-bit weights: the integer path keeps the exact fp32 parameters behind the rounded buffers."""
+    from omegaconf import OmegaConf
+    from qdiff.base.base_quantizer import StaticQuantizer
+    g = torch.Generator().manual_seed(0)
+    a, b = torch.randn(6, 64, generator=g).to(dev), (torch.randn(6, 64, generator=g) * 3).to(dev)
+    qz = StaticQuantizer(OmegaConf.create({"n_bits": 8, "sym": False}))
+    qz.init_quant_params(a)
+    qz.init_quant_params(b)
+    assert torch.equal(qz.x_max, torch.max(a.max(1)[0].clamp_min(0), b.max(1)[0].clamp_min(0)))
+    assert torch.equal(qz.x_min, torch.min(a.min(1)[0].clamp_max(0), b.min(1)[0].clamp_max(0)))
+    _, d, z = O.quant_rows(b.cpu(), 8, False, dynamic=False)
+    assert torch.equal(qz.delta.cpu(), d)
+    wb = (torch.randn(8, 128, generator=g) * 0.1).to(torch.bfloat16).to(dev)
+    qb = StaticQuantizer(OmegaConf.create({"n_bits": 8, "sym": False}))
+    deq = qb.forward(wb)
+    qo, do, zo = O.quant_rows(wb.float().cpu(), 8, False, dynamic=False)
+    d32, z32 = qb.params_f32(dev)
+    assert torch.equal(d32.cpu(), do.flatten()) and torch.equal(z32.cpu(), zo.flatten())
+    qb.init_done = True
+    assert torch.equal(qb.quantize_int8(wb).cpu().float(), qo.clamp(-128, 127))      # codes from the exact parameters
+    assert deq.dtype == torch.bfloat16 and qb.delta.dtype == torch.bfloat16

@@ -65,6 +65,8 @@ _SIGNATURES = {
     "b200q_attn_set_mode": (c_int, [c_int]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
+    "b200q_had_quant_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
+                                     c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                     c_int64, c_int64, c_void_p]),
 }
@@ -187,6 +189,28 @@ def dequant_rows(q, delta, zero_point=None, out_dtype=torch.float32):
                                    _ld(out), _stream())
     _check(rc, "b200q_dequant_rows")
     return out
+
+
+def had_quant_rows(x, colscale=None, hadK=None, K=1, log2_width=0, n_bits=8, want_rowsum=True, want_y=False, out=None):
+    """Fused smooth-scale + structured Hadamard rotation + per-token symmetric quantizer (include/b200q.h, f-2):
+    y = (x*colscale) . (H_K (x) H_{2^log2_width}) -> (codes int8, delta f32 [rows], rowsum int32 | None, y f32 | None)."""
+    x = _rows2d(x, "had_quant_rows")
+    if x.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        raise B200QError(f"had_quant_rows: unsupported dtype {x.dtype}")
+    rows, cols = x.shape
+    dev = x.device
+    q = out if out is not None else torch.empty((rows, cols), dtype=torch.int8, device=dev)
+    delta = torch.empty(rows, dtype=torch.float32, device=dev)
+    rs = torch.empty(rows, dtype=torch.int32, device=dev) if want_rowsum else None
+    y = torch.empty((rows, cols), dtype=torch.float32, device=dev) if want_y else None
+    for t, n, want in ((colscale, "colscale", cols), (hadK, "hadK", K * K)):
+        if t is not None and (not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != want):
+            raise B200QError(f"had_quant_rows: {n} must be a contiguous fp32 CUDA tensor of {want} elements")
+    rc = load().b200q_had_quant_rows(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(colscale), _ptr(hadK), int(K),
+                                     int(log2_width), int(n_bits), _ptr(q), _ld(q), _ptr(delta), _ptr(rs), _ptr(y),
+                                     _ld(y) if y is not None else 0, _stream())
+    _check(rc, "b200q_had_quant_rows")
+    return q, delta, rs, y
 
 
 # ---------------------------------------------------------------------------------------------

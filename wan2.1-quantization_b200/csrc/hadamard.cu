@@ -1,0 +1,291 @@
+// (f-2) ViDiT-Q / QuaRot / SmoothQuant activation pre-processing fused into the per-token quantizer:
+//
+//     y = (x * colscale) . (H_K (x) H_{2^m})            colscale[c] = channel_mask[c] * sign[c] / sqrt(n)
+//     q = rne(y / delta),  delta = max|y| / n_levels     (DynamicQuantizer sym, base_quantizer.py:110-157)
+//
+// Replaces `x = x*channel_mask; x = torch.matmul(x.double(), rotation_matrix)` followed by the activation quantizer
+// (ViDiT-Q/quant_utils/qdiff/viditq/viditq_quant_layer.py:58-66, quarot/quarot_quant_layer.py:55-62,
+// smooth_quant/sq_quant_layer.py:55-58): a dense fp64 [L, n] x [n, n] product per linear in the reference.  The rotation
+// R = diag(s) . H_n / sqrt(n) produced by random_hadamard_matrix (quarot_utils.py:186-192) is applied in its factored
+// form H_n = H_K (x) H_{2^m} (matmul_hadU, :158-179): a fast Walsh-Hadamard transform over the 2^m-wide segments of the
+// row (in registers + warp shuffles) and the order-K base block across the K segments.
+//
+// One CTA owns R rows in shared memory (fp32) and walks five phases: load*colscale -> FWHT (warp per segment) ->
+// K-block (thread per 4-column group, K inputs in registers) -> row abs-max -> quantize + store.  Several CTAs are
+// resident per SM, so the HBM phases of one overlap the arithmetic phases of another.  HBM-bound:
+// algorithmic bytes = rows*cols*(sizeof(in)+1) + 8*rows.
+#include "common.cuh"
+
+namespace b200q {
+
+struct HadArgs {
+  const void* x;
+  int64_t rows, cols, ldx;
+  const float* colscale;   // [cols] or null
+  const float* hadK;       // [K*K] row-major +-1, null iff K == 1
+  int K, log2w;            // cols == K << log2w ; log2w == 0: no transform at all (colscale only)
+  float n_levels;
+  int8_t* q; int64_t ldq;
+  float* delta; int32_t* rowsum;
+  float* y_out; int64_t ldy;
+  int R;                   // rows per CTA
+};
+
+constexpr int HAD_THREADS = 256;
+constexpr int HAD_KMAX = 32;
+
+// natural-order FWHT of one 32*E-wide segment held as E consecutive values per lane
+template <int E>
+__device__ __forceinline__ void fwht_segment(float* seg, int lane) {
+  float v[E];
+  if constexpr (E >= 4) {
+#pragma unroll
+    for (int i = 0; i < E; i += 4) {
+      const float4 t = *reinterpret_cast<const float4*>(seg + lane * E + i);
+      v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w;
+    }
+  } else if constexpr (E == 2) {
+    const float2 t = *reinterpret_cast<const float2*>(seg + lane * 2);
+    v[0] = t.x; v[1] = t.y;
+  } else {
+    v[0] = seg[lane];
+  }
+#pragma unroll
+  for (int h = 1; h < E; h <<= 1) {
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      if ((i & h) == 0) {
+        const float lo = v[i], hi = v[i + h];
+        v[i] = lo + hi; v[i + h] = lo - hi;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const bool upper = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < E; ++i) {
+      const float other = __shfl_xor_sync(0xffffffffu, v[i], o);
+      v[i] = upper ? other - v[i] : v[i] + other;
+    }
+  }
+  if constexpr (E >= 4) {
+#pragma unroll
+    for (int i = 0; i < E; i += 4)
+      *reinterpret_cast<float4*>(seg + lane * E + i) = make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]);
+  } else if constexpr (E == 2) {
+    *reinterpret_cast<float2*>(seg + lane * 2) = make_float2(v[0], v[1]);
+  } else {
+    seg[lane] = v[0];
+  }
+}
+
+// out[i][c..c+3] = sum_j h[i][j] * y[j][c..c+3], in place on one 4-column group (all K inputs are read first)
+template <int KM>
+__device__ __forceinline__ void kblock_group(float* base, int W, int K, const float2* s_h2) {
+  uint64_t y01[KM], y23[KM];
+#pragma unroll
+  for (int j = 0; j < KM; ++j) {
+    if (j < K) {
+      const float4 t = *reinterpret_cast<const float4*>(base + (size_t)j * W);
+      y01[j] = pack_f32x2(t.x, t.y); y23[j] = pack_f32x2(t.z, t.w);
+    } else {
+      y01[j] = 0; y23[j] = 0;
+    }
+  }
+  for (int i = 0; i < K; ++i) {
+    uint64_t a01 = 0, a23 = 0;                      // bit pattern of (0.f, 0.f)
+    const float2* hrow = s_h2 + i * K;
+#pragma unroll
+    for (int j = 0; j < KM; ++j) {
+      if (j < K) {
+        const float2 hh = hrow[j];                  // (h, h): broadcast LDS.64
+        const uint64_t h2 = pack_f32x2(hh.x, hh.y);
+        a01 = fma_f32x2(h2, y01[j], a01);
+        a23 = fma_f32x2(h2, y23[j], a23);
+      }
+    }
+    float o0, o1, o2, o3;
+    unpack_f32x2(a01, o0, o1); unpack_f32x2(a23, o2, o3);
+    *reinterpret_cast<float4*>(base + (size_t)i * W) = make_float4(o0, o1, o2, o3);
+  }
+}
+
+template <typename T, int KM>
+__global__ void __launch_bounds__(HAD_THREADS, KM <= 12 ? 3 : (KM <= 20 ? 2 : 1)) had_quant_kernel(const HadArgs a) {
+  using VT = Vec16<T>;
+  constexpr int N = VT::N;
+  extern __shared__ __align__(16) uint8_t had_smem[];
+  const int n = (int)a.cols, R = a.R, K = a.K;
+  float* buf = reinterpret_cast<float*>(had_smem);                       // [R][n]
+  float2* s_h2 = reinterpret_cast<float2*>(buf + (size_t)R * n);         // [K*K] (h, h)
+  int* s_amax = reinterpret_cast<int*>(s_h2 + K * K);                    // [R] fp32 bits (non-negative: int order == float order)
+  int* s_sum = s_amax + R;                                               // [R]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int W = 1 << a.log2w;
+  const int64_t row0 = (int64_t)blockIdx.x * R;
+
+  if (K > 1) for (int i = tid; i < K * K; i += HAD_THREADS) { const float h = a.hadK[i]; s_h2[i] = make_float2(h, h); }
+  if (tid < R) { s_amax[tid] = 0; s_sum[tid] = 0; }
+
+  // ---- phase 1: load, * colscale -> smem ----
+  const int kv = n / N;
+  for (int f = tid; f < R * kv; f += HAD_THREADS) {
+    const int r = f / kv, v = f - r * kv;
+    const int64_t row = row0 + r;
+    float x[N];
+    if (row < a.rows) {
+      VT::unpack(ldg_stream16(reinterpret_cast<const T*>(a.x) + row * a.ldx + (int64_t)v * N), x);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) x[i] = 0.f;
+    }
+    float* dst = buf + (size_t)r * n + v * N;
+#pragma unroll
+    for (int h = 0; h < N / 4; ++h) {
+      float4 o = make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+      if (a.colscale != nullptr) {
+        const float4 c = __ldg(reinterpret_cast<const float4*>(a.colscale + v * N + 4 * h));
+        o.x *= c.x; o.y *= c.y; o.z *= c.z; o.w *= c.w;
+      }
+      *reinterpret_cast<float4*>(dst + 4 * h) = o;
+    }
+  }
+  __syncthreads();
+
+  // ---- phase 2: FWHT over every 2^m-wide segment (one warp per segment) ----
+  if (a.log2w > 0) {
+    const int nseg = R * K;
+    for (int s = warp; s < nseg; s += HAD_THREADS / 32) {
+      float* seg = buf + (size_t)s * W;               // segments of a row are contiguous, rows are contiguous
+      switch (a.log2w) {
+        case 5: fwht_segment<1>(seg, lane); break;
+        case 6: fwht_segment<2>(seg, lane); break;
+        case 7: fwht_segment<4>(seg, lane); break;
+        default: fwht_segment<8>(seg, lane); break;   // 8
+      }
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 3: order-K base block across the segments ----
+  if (K > 1) {
+    const int G = W >> 2;
+    for (int it = tid; it < R * G; it += HAD_THREADS) {
+      const int r = it / G, c = it - r * G;
+      float* base = buf + (size_t)r * n + c * 4;
+      kblock_group<KM>(base, W, K, s_h2);
+    }
+    __syncthreads();
+  }
+
+  // ---- phase 4: per-row abs-max (n % 128 == 0: the 32 float4 of a warp iteration lie in one row) ----
+  const int n4 = n >> 2;
+  for (int f = tid; f < R * n4; f += HAD_THREADS) {
+    const float4 t = *reinterpret_cast<const float4*>(buf + (size_t)f * 4);
+    float m = fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w)));
+    m = warp_max(m);
+    if (lane == 0) atomicMax(&s_amax[f / n4], __float_as_int(m));
+  }
+  __syncthreads();
+
+  // ---- phase 5: quantize + store ----
+  for (int f = tid; f < R * n4; f += HAD_THREADS) {
+    const int r = f / n4, v = f - r * n4;
+    const int64_t row = row0 + r;
+    float delta = __fdiv_rn(__int_as_float(s_amax[r]), a.n_levels);
+    if (delta < 1.0e-6f) delta = 1.0e-6f;                                // base_quantizer.py:122-128
+    const float rc = __frcp_rn(delta);
+    const float4 t = *reinterpret_cast<const float4*>(buf + (size_t)f * 4);
+    const uint64_t r2 = pack_f32x2(rc, rc), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+    uint32_t c0, c1, c2, c3;
+    unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.x, t.y), nd2, r2, magic2), c0, c1);
+    unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.z, t.w), nd2, r2, magic2), c2, c3);
+    const uint32_t packed = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+    int sum = __dp4a((int)packed, 0x01010101, 0);
+    if (row < a.rows) {
+      stg_stream4(a.q + row * a.ldq + (int64_t)v * 4, packed);
+      if (a.y_out != nullptr) *reinterpret_cast<float4*>(a.y_out + row * a.ldy + (int64_t)v * 4) = t;
+    }
+    if (a.rowsum != nullptr) {
+      sum = warp_sum(sum);
+      if (lane == 0) atomicAdd(&s_sum[r], sum);
+    }
+  }
+  __syncthreads();
+  if (tid < R && row0 + tid < a.rows) {
+    float delta = __fdiv_rn(__int_as_float(s_amax[tid]), a.n_levels);
+    if (delta < 1.0e-6f) delta = 1.0e-6f;
+    a.delta[row0 + tid] = delta;
+    if (a.rowsum != nullptr) a.rowsum[row0 + tid] = s_sum[tid];
+  }
+}
+
+template <typename T, int KM>
+static int launch_had_km(const HadArgs& a0, cudaStream_t st) {
+  HadArgs a = a0;
+  const int n = (int)a.cols;
+  const int W = 1 << a.log2w;
+  // rows per CTA: enough 4-column groups for 256 threads in the K-block phase, within ~96 KB of shared memory
+  int R = 8;
+  while (R > 1 && (size_t)R * n * 4 > 98304) R >>= 1;
+  if (a.K > 1) while (R > 1 && R * (W / 4) > 2 * HAD_THREADS && (size_t)R * n * 4 > 49152) R >>= 1;
+  a.R = R;
+  const size_t smem = (size_t)R * n * 4 + (size_t)a.K * a.K * 8 + (size_t)R * 8 + 16;
+  B200Q_REQUIRE(smem <= 232448, B200Q_ERR_UNSUPPORTED, "had_quant_rows: cols=%d does not fit in shared memory", n);
+  static bool configured = false;
+  if (!configured) {
+    B200Q_CUDA_OK(cudaFuncSetAttribute(had_quant_kernel<T, KM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448));
+    configured = true;
+  }
+  const unsigned grid = (unsigned)((a.rows + R - 1) / R);
+  had_quant_kernel<T, KM><<<grid, HAD_THREADS, smem, st>>>(a);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
+template <typename T>
+static int launch_had(const HadArgs& a, cudaStream_t st) {
+  if (a.K <= 12) return launch_had_km<T, 12>(a, st);
+  if (a.K <= 20) return launch_had_km<T, 20>(a, st);
+  return launch_had_km<T, HAD_KMAX>(a, st);
+}
+
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_had_quant_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                                    const float* colscale, const float* hadK, int K, int log2_width, int n_bits,
+                                    int8_t* q, int64_t ldq, float* delta, int32_t* rowsum, float* y_out, int64_t ldy,
+                                    b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "had_quant_rows: negative shape");
+  if (rows == 0 || cols == 0) return B200Q_OK;
+  B200Q_REQUIRE(x && q && delta, B200Q_ERR_BAD_ARG, "had_quant_rows: null pointer");
+  B200Q_REQUIRE(n_bits >= 2 && n_bits <= 8, B200Q_ERR_BAD_ARG, "had_quant_rows: n_bits=%d out of [2,8]", n_bits);
+  B200Q_REQUIRE(K >= 1 && K <= HAD_KMAX, B200Q_ERR_UNSUPPORTED, "had_quant_rows: base block order K=%d not in [1,%d]", K, HAD_KMAX);
+  B200Q_REQUIRE((K == 1) == (hadK == nullptr), B200Q_ERR_BAD_ARG, "had_quant_rows: hadK is given iff K > 1");
+  B200Q_REQUIRE(log2_width == 0 || (log2_width >= 5 && log2_width <= 8), B200Q_ERR_UNSUPPORTED,
+                "had_quant_rows: segment width 2^%d not in {1 (no transform), 32..256}", log2_width);
+  B200Q_REQUIRE(log2_width != 0 || K == 1, B200Q_ERR_BAD_ARG, "had_quant_rows: log2_width == 0 means no transform (K must be 1)");
+  B200Q_REQUIRE(log2_width == 0 || cols == ((int64_t)K << log2_width), B200Q_ERR_BAD_ARG,
+                "had_quant_rows: cols=%lld != K * 2^log2_width", (long long)cols);
+  B200Q_REQUIRE(cols % 128 == 0 && cols <= 57344, B200Q_ERR_UNSUPPORTED, "had_quant_rows: cols must be a multiple of 128, <= 57344");
+  const int vecn = x_dtype == B200Q_F32 ? 4 : 8;
+  B200Q_REQUIRE(x_dtype >= B200Q_F32 && x_dtype <= B200Q_F16, B200Q_ERR_BAD_ARG, "had_quant_rows: bad x_dtype");
+  B200Q_REQUIRE(ldx >= cols && ldx % vecn == 0 && aligned(x, 16), B200Q_ERR_UNSUPPORTED, "had_quant_rows: x misaligned");
+  B200Q_REQUIRE(ldq >= cols && ldq % 4 == 0 && aligned(q, 4), B200Q_ERR_UNSUPPORTED, "had_quant_rows: q misaligned");
+  B200Q_REQUIRE(!colscale || aligned(colscale, 16), B200Q_ERR_BAD_ARG, "had_quant_rows: colscale must be 16-byte aligned");
+  B200Q_REQUIRE(!y_out || (ldy >= cols && ldy % 4 == 0 && aligned(y_out, 16)), B200Q_ERR_BAD_ARG, "had_quant_rows: y_out misaligned");
+  HadArgs a{};
+  a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.colscale = colscale; a.hadK = hadK; a.K = K; a.log2w = log2_width;
+  a.n_levels = (float)((1 << (n_bits - 1)) - 1);
+  a.q = q; a.ldq = ldq; a.delta = delta; a.rowsum = rowsum; a.y_out = y_out; a.ldy = ldy;
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (x_dtype) {
+    case B200Q_F32: return launch_had<float>(a, st);
+    case B200Q_BF16: return launch_had<__nv_bfloat16>(a, st);
+    default: return launch_had<__half>(a, st);
+  }
+}

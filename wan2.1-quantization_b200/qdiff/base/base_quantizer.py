@@ -63,15 +63,30 @@ class BaseQuantizer(nn.Module):
         back = (lambda t: t.to(home)) if home is not None else (lambda t: t)
         self.delta = back(delta).unsqueeze(-1).to(x.dtype)
         self.zero_point = back(zp).unsqueeze(-1).to(x.dtype)
+        # the kernel derives the codes from fp32 parameters; for 16-bit inputs `delta` / `zero_point` above are rounded
+        # to x.dtype (the reference's buffers have x's dtype), so the exact pair is kept for the integer path
+        # (QuantizedLinear.int_weight_state): codes == the codes behind the fake-quant weight, bit for bit
+        self._delta_f32, self._zp_f32, self._f32_of = back(delta), back(zp), self.delta
         if self.sym:
             self.x_absmax = back(smax)
         else:
             self.x_max, self.x_min = back(smax), back(smin)
         return q, delta, zp, rowsum, home
 
+    def params_f32(self, device):
+        """(delta, zero_point) fp32 [G] on `device`: the exact kernel parameters while `delta` is still the tensor they
+        produced, else the (possibly loaded) buffers."""
+        if getattr(self, "_f32_of", None) is self.delta and self.delta is not None:
+            d, z = self._delta_f32, self._zp_f32
+        else:
+            d, z = self.delta, self.zero_point
+        return (d.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous(),
+                z.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous())
+
     def _apply_static(self, x):
         xc, home = _on_cuda(x.detach())
-        q, _ = b200q.quant_rows_static(xc, self.delta.to(xc.device), self.zero_point.to(xc.device), self.n_bits, self.sym)
+        d, z = self.params_f32(xc.device)
+        q, _ = b200q.quant_rows_static(xc, d, z, self.n_bits, self.sym)
         return q, home
 
     @staticmethod
@@ -83,6 +98,7 @@ class BaseQuantizer(nn.Module):
 
     def _dequant(self, q, like, home):
         dev = q.device
+        # fake-quant output = (q + zp) * delta with the buffers as the reference holds them (x's dtype)
         out = b200q.dequant_rows(q, self.delta.to(dev), self.zero_point.to(dev), like.dtype)
         return out.to(home) if home is not None else out
 
@@ -105,29 +121,35 @@ class StaticQuantizer(BaseQuantizer):
             self.x_min = None
 
     def init_quant_params(self, x):
+        """base_quantizer.py:70-99: delta / zero_point come from THIS call's rows; the stored statistics x_absmax /
+        x_max / x_min are running maxima / minima over calls (:76, :84, :88)."""
+        prev = (self.x_absmax,) if self.sym else (self.x_max, self.x_min)
         self._compute(x, dynamic=False)
+        if prev[0] is not None and prev[0].shape == (self.x_absmax if self.sym else self.x_max).shape:
+            if self.sym:
+                self.x_absmax = torch.max(self.x_absmax, prev[0].to(self.x_absmax.device))
+            else:
+                self.x_max = torch.max(self.x_max, prev[0].to(self.x_max.device))
+                self.x_min = torch.min(self.x_min, prev[1].to(self.x_min.device))
         if not bool(torch.all(self.delta > 1.0e-6)):
             logger.warning("unexpected small delta exists in %s (min %.3e)", self.module_name, float(self.delta.min()))
 
     def quantize_int8(self, x):
         """-> int8 codes [G, C] on the CUDA device (base_quantizer.py:63-68 without the float detour)."""
         if self.init_done is not True:
-            q, _, _, _, _ = self._compute(x, dynamic=False)
-            return q
+            self.init_quant_params(x)
         return self._apply_static(x)[0]
 
     def quantize(self, x: torch.Tensor):
         if self.init_done is not True:
-            q, _, _, _, home = self._compute(x, dynamic=False)
-        else:
-            q, home = self._apply_static(x)
+            self.init_quant_params(x)
+        q, home = self._apply_static(x)
         return self._codes_as(q, x, home)
 
     def forward(self, x: torch.Tensor):
         if self.init_done is not True:
-            q, _, _, _, home = self._compute(x, dynamic=False)
-        else:
-            q, home = self._apply_static(x)
+            self.init_quant_params(x)
+        q, home = self._apply_static(x)
         return self._dequant(q, x, home)
 
 

@@ -27,6 +27,47 @@ def _is_list(v):
     return isinstance(v, (list, tuple)) or bool(ListConfig and isinstance(v, ListConfig))
 
 
+class ActPlan:
+    """What a layer does to its activations in front of the per-token quantizer, in the factored form the fused kernel
+    b200q_had_quant_rows takes (include/b200q.h):  y = (x * colscale) . (H_K (x) H_{2^log2w}),
+    colscale = channel_mask * sign / sqrt(n).  `mask` / `sign` keep the un-folded factors for the int-weight checkpoint."""
+
+    def __init__(self, n, colscale, hadK, K, log2w, mask=None, sign=None):
+        self.n, self.colscale, self.hadK, self.K, self.log2w, self.mask, self.sign = n, colscale, hadK, K, log2w, mask, sign
+
+    @staticmethod
+    def rotation(n, sign, mask, device):
+        """R = diag(sign) . H_n / sqrt(n), optionally after the smooth scale `mask`; None if the kernel cannot serve n."""
+        from qdiff.quarot.quarot_utils import hadamard_kernel_plan
+        kp = hadamard_kernel_plan(n)
+        if kp is None:
+            return None
+        K, w, H = kp
+        cs = sign.detach().double().cpu().reshape(-1) / (n ** 0.5)
+        if mask is not None:
+            cs = cs * mask.detach().double().cpu().reshape(-1)
+        hadK = None if H is None else H.to(torch.float32).reshape(-1).contiguous().to(device)
+        return ActPlan(n, cs.to(torch.float32).contiguous().to(device), hadK, K, w,
+                       None if mask is None else mask.detach().float().reshape(-1).cpu(), sign.detach().float().reshape(-1).cpu())
+
+    @staticmethod
+    def scale_only(mask, device):
+        n = mask.numel()
+        if n % 128 != 0:
+            return None
+        m = mask.detach().float().reshape(-1)
+        return ActPlan(n, m.contiguous().to(device), None, 1, 0, m.cpu(), None)
+
+    def to(self, device):
+        return ActPlan(self.n, self.colscale.to(device), None if self.hadK is None else self.hadK.to(device), self.K,
+                       self.log2w, self.mask, self.sign)
+
+    def quantize(self, x2d, n_bits=8, want_rowsum=True):
+        """-> (codes int8 [rows, n], delta f32 [rows], rowsum int32 [rows] | None)"""
+        q, d, rs, _ = b200q.had_quant_rows(x2d, self.colscale, self.hadK, self.K, self.log2w, n_bits, want_rowsum=want_rowsum)
+        return q, d, rs
+
+
 class QuantizedLinear(torch.nn.Linear):
     """Static per-out-channel weight quantization + dynamic per-token activation quantization."""
 
@@ -74,8 +115,9 @@ class QuantizedLinear(torch.nn.Linear):
         if st is not None and st["device"] == device and st["n_bits"] == wq.n_bits and st["delta_id"] is wq.delta:
             return st
         w = self._weight_for_codes().detach().to(device)
-        delta = wq.delta.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
-        zp = wq.zero_point.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous()
+        delta, zp = wq.params_f32(device) if hasattr(wq, "params_f32") else (
+            wq.delta.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous(),
+            wq.zero_point.detach().to(device=device, dtype=torch.float32).reshape(-1).contiguous())
         codes, _ = b200q.quant_rows_static(w, delta, zp, wq.n_bits, wq.sym)
         K = codes.shape[1]
         if K % 16 != 0:                    # TMA row pitch: pad the K axis with zero codes once, view back to K
@@ -99,7 +141,12 @@ class QuantizedLinear(torch.nn.Linear):
         return x.dtype if x.dtype in (torch.float32, torch.bfloat16, torch.float16) else torch.float32
 
     def _prepare_activation(self, x2d):
-        return x2d        # hook for the smooth/rotate variants
+        return x2d        # hook for the smooth/rotate variants (unfused form: torch ops in front of the quantizer)
+
+    def _act_plan(self, device):
+        """ActPlan for the fused smooth/rotate + quantize kernel, or None: plain layer / transform the kernel cannot
+        serve (then `_prepare_activation` runs in front of the row quantizer)."""
+        return None
 
     def forward(self, x: torch.Tensor, *args, **kwargs) -> torch.Tensor:
         """x: [B, N_token, C] (any leading shape is accepted) -> [B, N_token, C_out]"""
@@ -117,9 +164,13 @@ class QuantizedLinear(torch.nn.Linear):
             raise NotImplementedError(
                 "asymmetric activation quantization needs the zp_a*colsum(W) epilogue term, which libb200q does not "
                 "implement; the Wan2.1 configs use symmetric per-token activations (quant_configs/config.yaml:17-18)")
-        x2d = self._prepare_activation(x2d)
         st = self.int_weight_state(x2d.device)
-        qa, da, _, rowsum = self.a_quantizer.quantize_int8(x2d, want_rowsum=True)
+        plan = self._act_plan(x2d.device) if x2d.shape[1] % 16 == 0 else None
+        if plan is not None:
+            qa, da, rowsum = plan.quantize(x2d, self.a_quantizer.n_bits)
+        else:
+            x2d = self._prepare_activation(x2d)
+            qa, da, _, rowsum = self.a_quantizer.quantize_int8(x2d, want_rowsum=True)
         K = x2d.shape[1]
         if K % 16 != 0:
             padded = torch.zeros((qa.shape[0], (K + 15) // 16 * 16), dtype=torch.int8, device=qa.device)

@@ -10,7 +10,8 @@ quantizer kernel is the remaining step of SURVEY §8 f-2."""
 import torch
 
 from qdiff.base.quant_layer import QuantizedLinear
-from qdiff.quarot.quarot_utils import matmul_hadU, random_hadamard_matrix
+from qdiff.base.quant_layer import ActPlan
+from qdiff.quarot.quarot_utils import hadamard_kernel_plan, matmul_hadU, random_hadamard_matrix
 
 
 class RotationMixin:
@@ -33,6 +34,25 @@ class RotationMixin:
         if torch.allclose(s.view(-1, 1) * Hn, R.double(), atol=1e-9):
             return ("structured", s.float(), R)
         return ("dense", R.float(), R)
+
+    def rotation_sign(self):
+        """s of R = diag(s) . H_n / sqrt(n) (float32 [n]) for a structured rotation, else None."""
+        plan = getattr(self, "_rot_plan", None)
+        if plan is None or plan[2] is not self.rotation_matrix:
+            plan = self._rot_plan = self._plan_rotation()
+        return plan[1] if plan[0] == "structured" else None
+
+    def _rotation_act_plan(self, device, mask=None):
+        """ActPlan of x -> (x * mask) @ R for the fused kernel, or None (dense rotation / unsupported size)."""
+        cached = getattr(self, "_act_plan_cache", None)
+        if cached is not None and cached[0] is self.rotation_matrix and cached[1] is mask and cached[2] == device:
+            return cached[3]
+        plan = None
+        s = self.rotation_sign()
+        if s is not None:
+            plan = ActPlan.rotation(self.in_features, s, mask, device)
+        self._act_plan_cache = (self.rotation_matrix, mask, device, plan)
+        return plan
 
     def _rotate(self, x2d):
         plan = getattr(self, "_rot_plan", None)
@@ -64,3 +84,6 @@ class QuarotQuantizedLinear(RotationMixin, QuantizedLinear):
 
     def _prepare_activation(self, x2d):
         return self._rotate(x2d)
+
+    def _act_plan(self, device):
+        return self._rotation_act_plan(device)

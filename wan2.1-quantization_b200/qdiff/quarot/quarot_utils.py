@@ -138,6 +138,30 @@ def matmul_hadU(X, transpose=False):
     return y.reshape(X.shape) / math.sqrt(n)
 
 
+def hadamard_kernel_plan(n):
+    """Factorisation b200q_had_quant_rows accepts (include/b200q.h): n = K' * 2^w with w in [5, 8], K' <= 32 and
+    n % 128 == 0 -> (K', w, H_K' [K', K'] float64 or None when K' == 1); None when the fused kernel cannot serve n.
+    When the power-of-two part of n exceeds 2^8 the surplus Sylvester factor moves into the base block:
+    H_n = H_K (x) H_{2^m} = (H_K (x) H_{2^(m-8)}) (x) H_{2^8}."""
+    try:
+        K, m = hadamard_factor(n)
+    except ValueError:
+        return None
+    if n % 128 != 0 or m < 5:
+        return None
+    H = base_hadamard(K)
+    if m > 8:
+        extra = m - 8
+        S = torch.ones(1, 1, dtype=torch.float64)
+        for _ in range(extra):
+            S = torch.kron(base_hadamard(2), S)
+        H = torch.kron(H, S)
+        K, m = K << extra, 8
+    if K > 32:
+        return None
+    return K, m, (None if K == 1 else H.contiguous())
+
+
 def matmul_hadUt(X):
     return matmul_hadU(X, transpose=True)
 

@@ -8,7 +8,7 @@ The per-channel multiply is one elementwise pass in front of the row quantizer (
 the remaining step of SURVEY §8 f-2)."""
 import torch
 
-from qdiff.base.quant_layer import QuantizedLinear
+from qdiff.base.quant_layer import ActPlan, QuantizedLinear
 
 
 class SQQuantizedLinear(QuantizedLinear):
@@ -41,3 +41,11 @@ class SQQuantizedLinear(QuantizedLinear):
         if self.channel_mask is None:
             raise RuntimeError("SQQuantizedLinear: channel_mask not set (run PTQ or load_quant_param_dict first)")
         return x2d * self.channel_mask.to(device=x2d.device, dtype=x2d.dtype).reshape(1, -1)
+
+    def _act_plan(self, device):
+        if self.channel_mask is None:
+            raise RuntimeError("SQQuantizedLinear: channel_mask not set (run PTQ or load_quant_param_dict first)")
+        cached = getattr(self, "_act_plan_cache", None)
+        if cached is None or cached[0] is not self.channel_mask or cached[1] != device:
+            cached = self._act_plan_cache = (self.channel_mask, device, ActPlan.scale_only(self.channel_mask, device))
+        return cached[2]

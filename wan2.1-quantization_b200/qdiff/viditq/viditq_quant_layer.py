@@ -44,3 +44,8 @@ class ViDiTQuantizedLinear(RotationMixin, QuantizedLinear):
         if self.channel_mask is None:
             raise RuntimeError("ViDiTQuantizedLinear: channel_mask not set (run PTQ or load_quant_param_dict first)")
         return self._rotate(x2d * self.channel_mask.to(device=x2d.device, dtype=x2d.dtype).reshape(1, -1))
+
+    def _act_plan(self, device):
+        if self.channel_mask is None:
+            raise RuntimeError("ViDiTQuantizedLinear: channel_mask not set (run PTQ or load_quant_param_dict first)")
+        return self._rotation_act_plan(device, self.channel_mask)

@@ -20,43 +20,49 @@ import math
 import torch
 
 import b200q
-from .model import QWeight, WanBlockQ, WanConfig, WanDiTQ
+from .model import LINEARS, DenseRotation, FPWeight, QWeight, WanBlockQ, WanConfig, WanDiTQ
 
 META_KEY = "__b200q_meta__"
-_PREFIXES = ("_fsdp_wrapped_module.", "module.", "_orig_mod.")
+_WRAPPERS = {"_fsdp_wrapped_module", "module", "_orig_mod"}
 
 
 def strip_wrapper_prefixes(name: str) -> str:
-    parts = name
-    changed = True
-    while changed:
-        changed = False
-        for p in _PREFIXES:
-            if p in parts:
-                parts = parts.replace(p, "")
-                changed = True
-    return parts
+    """Drop FSDP / DDP / torch.compile wrapper COMPONENTS of a dotted key (whole path components only: `fp_module.` is
+    not `module.`)."""
+    return ".".join(p for p in name.split(".") if p not in _WRAPPERS)
 
 
 def export_int_state_dict(model, device=None) -> dict:
-    """state_dict of `model` with every qdiff QuantizedLinear replaced by its integer form (keys above)."""
+    """state_dict of `model` with every qdiff QuantizedLinear replaced by its integer form (keys above).  Layers the
+    config keeps in floating point (remain_fp_regex: never wrapped; mixed-precision index 0: `quant_mode` False) keep
+    their FP weight.  SmoothQuant / QuaRot / ViDiT-Q layers also store what they apply to their activations:
+    `<layer>.channel_mask` (fp32 [C_in]) and `<layer>.rotation_sign` (int8 [C_in], R = diag(sign).H_n/sqrt(n)) or, for a
+    rotation that is not of that form, the dense `<layer>.rotation_matrix` - the codes are those of the scaled / rotated
+    weight, so the runtime must apply the same transform (reference defect B-4, SURVEY appendix B: its exporter drops
+    it)."""
     from qdiff.base.quant_layer import QuantizedLinear
     dev = device or torch.device("cuda", torch.cuda.current_device())
     sd = {}
-    qnames = {}
+    qnames, fpnames = {}, {}
     for name, mod in model.named_modules():
-        if isinstance(mod, QuantizedLinear) and mod.w_quantizer is not None:
-            qnames[strip_wrapper_prefixes(name)] = mod
+        if isinstance(mod, QuantizedLinear):
+            if mod.w_quantizer is not None and mod.a_quantizer is not None and mod.quant_mode:
+                qnames[strip_wrapper_prefixes(name)] = mod
+            else:
+                fpnames[strip_wrapper_prefixes(name)] = mod
     for k, v in model.state_dict().items():
-        k = strip_wrapper_prefixes(k)
         if "fp_weight" in k or "fp_module" in k or ".w_quantizer." in k or ".a_quantizer." in k:
             continue
+        k = strip_wrapper_prefixes(k)
         layer = k.rsplit(".", 1)[0]
-        if layer in qnames and k.endswith(".weight"):
+        if (layer in qnames or layer in fpnames) and k.endswith(".weight"):
             continue                                   # replaced below
         sd[k] = v.detach().cpu()
-    bits = {}
+    for name, mod in fpnames.items():
+        sd[f"{name}.weight"] = mod.fp_module.weight.detach().cpu()
+    bits, infeat = {}, {}
     for name, mod in qnames.items():
+        infeat[name] = int(mod.in_features)
         st = mod.int_weight_state(dev)
         if st["packed"] is not None:
             sd[f"{name}.weight_packed"] = st["packed"].contiguous().cpu()
@@ -66,13 +72,14 @@ def export_int_state_dict(model, device=None) -> dict:
         if st["zp"] is not None:
             sd[f"{name}.zp_weight"] = st["zp"].cpu()
         bits[name] = int(st["n_bits"])
-        variant = {}
         if getattr(mod, "channel_mask", None) is not None:
-            variant["channel_mask"] = mod.channel_mask.detach().float().cpu()
+            sd[f"{name}.channel_mask"] = mod.channel_mask.detach().float().cpu()
         if getattr(mod, "rotation_matrix", None) is not None:
-            variant["rotation_matrix"] = mod.rotation_matrix.detach().cpu()
-        for kk, vv in variant.items():
-            sd[f"{name}.{kk}"] = vv
+            sign = mod.rotation_sign() if hasattr(mod, "rotation_sign") else None
+            if sign is not None:
+                sd[f"{name}.rotation_sign"] = sign.detach().cpu().to(torch.int8)
+            else:
+                sd[f"{name}.rotation_matrix"] = mod.rotation_matrix.detach().float().cpu()
     # the reference's general LayerNorm kernel wants explicit unit weights (quant_wanx.py:170-175)
     blocks = sorted({int(k.split(".")[1]) for k in sd if k.startswith("blocks.") and k.split(".")[1].isdigit()})
     for i in blocks:
@@ -80,8 +87,8 @@ def export_int_state_dict(model, device=None) -> dict:
         if dim is not None:
             sd.setdefault(f"blocks.{i}.norm1.weight", torch.ones(dim))
             sd.setdefault(f"blocks.{i}.norm2.weight", torch.ones(dim))
-    sd[META_KEY] = {"format": "b200q-int-weight", "version": 1, "scale_dtype": "float32", "weight_bits": bits,
-                    "w4_packing": "b200q_pack_w4"}
+    sd[META_KEY] = {"format": "b200q-int-weight", "version": 2, "scale_dtype": "float32", "weight_bits": bits,
+                    "in_features": infeat, "w4_packing": "b200q_pack_w4"}
     return sd
 
 
@@ -91,17 +98,52 @@ def save_int_checkpoint(model, path, device=None):
     return sd
 
 
-def _qweight(sd, name, device):
-    """<name>.{weight|weight_packed, scale_weight, zp_weight, bias} -> QWeight on `device`."""
+def _act_transform(sd, name, n, device):
+    """<name>.{channel_mask, rotation_sign | rotation_matrix} -> the activation transform the runtime applies in front
+    of the layer's quantizer (fused kernel plan where the size allows, dense fp32 product otherwise), or None."""
+    from qdiff.base.quant_layer import ActPlan
+    mask = sd.get(f"{name}.channel_mask")
+    sign = sd.get(f"{name}.rotation_sign")
+    R = sd.get(f"{name}.rotation_matrix")
+    if mask is None and sign is None and R is None:
+        return None
+    if R is not None:
+        return DenseRotation(R, mask, device)
+    if sign is not None:
+        plan = ActPlan.rotation(n, sign.float(), mask, device)
+        if plan is not None:
+            return plan
+        from qdiff.quarot.quarot_utils import matmul_hadU
+        return DenseRotation(matmul_hadU(torch.diag(sign.double())), mask, device)
+    plan = ActPlan.scale_only(mask, device)
+    return plan if plan is not None else DenseRotation(None, mask, device)
+
+
+def _layer(sd, name, device):
+    """<name>.{weight | weight_packed, scale_weight, zp_weight, bias, ...} -> QWeight, or FPWeight for a layer the
+    checkpoint keeps in floating point."""
     meta = sd.get(META_KEY, {})
+    bias = sd.get(f"{name}.bias")
+    if f"{name}.scale_weight" not in sd:
+        w = sd.get(f"{name}.weight")
+        if w is None or not w.dtype.is_floating_point:
+            raise b200q.B200QError(f"{name}: neither an integer layer (scale_weight missing) nor an FP weight in the checkpoint")
+        return FPWeight(w, bias)
     n_bits = meta.get("weight_bits", {}).get(name, 8)
     delta = sd[f"{name}.scale_weight"].to(device=device, dtype=torch.float32).reshape(-1).contiguous()
     zp = sd.get(f"{name}.zp_weight")
     zp = None if zp is None else zp.to(device=device, dtype=torch.float32).reshape(-1).contiguous()
-    bias = sd.get(f"{name}.bias")
     bias = None if bias is None else bias.to(device=device, dtype=torch.float32).contiguous()
     if f"{name}.weight_packed" in sd:
-        raise NotImplementedError("packed 4-bit layers are loaded through their int8 codes: export with codes present")
+        packed = sd[f"{name}.weight_packed"]
+        if packed.dtype != torch.uint8:
+            raise b200q.B200QError(f"{name}.weight_packed is {packed.dtype}, expected uint8 (b200q_pack_w4 format)")
+        nbytes = packed.shape[1]
+        K = meta.get("in_features", {}).get(name, nbytes * 2)           # 8 codes per 4 bytes
+        pitch = (nbytes + 15) // 16 * 16                                 # TMA global stride: multiple of 16 bytes
+        buf = torch.zeros((packed.shape[0], pitch), dtype=torch.uint8, device=device)
+        buf[:, :nbytes] = packed.to(device)
+        return QWeight(None, delta, zp, bias, n_bits, buf[:, :nbytes], K=K, pre=_act_transform(sd, name, K, device))
     codes = sd[f"{name}.weight"]
     if codes.dtype != torch.int8:
         raise b200q.B200QError(f"{name}.weight is {codes.dtype}, expected int8 codes (is this an FP checkpoint?)")
@@ -112,30 +154,23 @@ def _qweight(sd, name, device):
         padded[:, :K] = codes
         codes = padded[:, :K]
     packed = b200q.pack_w4(codes) if n_bits <= 4 else None
-    return QWeight(codes, delta, zp, bias, n_bits, packed)
+    return QWeight(codes, delta, zp, bias, n_bits, packed, pre=_act_transform(sd, name, K, device))
 
 
 def dit_from_int_state_dict(cfg: WanConfig, sd: dict, device=None, sp=None, attn_quant=False) -> WanDiTQ:
     """Build the integer runtime (wan_b200.model.WanDiTQ) from an int-weight state dict: the counterpart of
     hardware_forward_refactor's step (3) (quant_wanx.py:221-228).  FP parts (patch/text/time embeddings, head) are taken
-    as stored (remain_fp_regex keeps them FP, quant_configs/config.yaml:9)."""
+    as stored (remain_fp_regex keeps them FP, quant_configs/config.yaml:9); block linears are integer or FP layer by
+    layer, as the checkpoint has them."""
     dev = device or torch.device("cuda", torch.cuda.current_device())
-    sd = {strip_wrapper_prefixes(k): v for k, v in sd.items()}
+    sd = {(k if k == META_KEY else strip_wrapper_prefixes(k)): v for k, v in sd.items()}
     f32 = lambda k: sd[k].to(device=dev, dtype=torch.float32).contiguous()
     bf = lambda k: sd[k].to(device=dev, dtype=torch.bfloat16).contiguous()
     blocks = []
     for i in range(cfg.num_layers):
         b = f"blocks.{i}."
-        q = lambda n: _qweight(sd, b + n, dev)
-        w = {
-            "self_attn.qkv": QWeight.cat([q("self_attn.q"), q("self_attn.k"), q("self_attn.v")]),
-            "self_attn.o": q("self_attn.o"),
-            "cross_attn.q": q("cross_attn.q"),
-            "cross_attn.kv": QWeight.cat([q("cross_attn.k"), q("cross_attn.v")]),
-            "cross_attn.o": q("cross_attn.o"),
-            "ffn.0": q("ffn.0"), "ffn.2": q("ffn.2"),
-            "modulation": f32(b + "modulation"),
-        }
+        w = {n: _layer(sd, b + n, dev) for n in LINEARS}
+        w["modulation"] = f32(b + "modulation")
         for k in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight",
                   "cross_attn.norm_k.weight", "norm3.weight", "norm3.bias"):
             if b + k in sd:

@@ -65,10 +65,14 @@ class QWeight:
     """int8 (or packed int4) codes [N,K] + fp32 per-out-channel delta / zero_point + fp32 bias: what
     `quantize_and_save_weight_` exports (quant_wanx_cuda.py:39-55), kept in fp32 scales to match the fake-quant path."""
 
-    def __init__(self, codes, delta, zp, bias, n_bits=8, packed=None, K=None):
+    def __init__(self, codes, delta, zp, bias, n_bits=8, packed=None, K=None, pre=None):
+        """codes may be None for a 4-bit layer that only carries `packed` (loaded from a W4 checkpoint).  `pre`: what
+        the layer applies to its activations in front of the per-token quantizer (SmoothQuant / QuaRot / ViDiT-Q): an
+        object with quantize(x2d, n_bits) -> (codes, delta, rowsum), e.g. qdiff.base.quant_layer.ActPlan."""
         self.codes, self.delta, self.zp, self.bias, self.n_bits, self.packed = codes, delta, zp, bias, n_bits, packed
         self.N = codes.shape[0] if codes is not None else packed.shape[0]
         self.K = K if K is not None else codes.shape[1]
+        self.pre = pre
 
     @staticmethod
     def from_fp(weight, bias, n_bits=8, sym=False):
@@ -82,19 +86,30 @@ class QWeight:
     @staticmethod
     def from_quantized_linear(layer):
         """Build from a qdiff QuantizedLinear (after PTQ / load_quant_param_dict)."""
-        st = layer.int_weight_state(torch.device("cuda", torch.cuda.current_device()))
+        dev = torch.device("cuda", torch.cuda.current_device())
+        st = layer.int_weight_state(dev)
         b = None if layer.bias is None else layer.bias.detach().float().cuda().contiguous()
-        return QWeight(st["codes"], st["delta"], st["zp"], b, st["n_bits"], st["packed"])
+        return QWeight(st["codes"], st["delta"], st["zp"], b, st["n_bits"], st["packed"], pre=act_transform_of(layer, dev))
 
     @staticmethod
     def cat(ws):
         """Stack along N (q|k|v share their activation codes -> one GEMM)."""
-        assert all(w.n_bits == ws[0].n_bits and w.K == ws[0].K for w in ws)
-        codes = torch.cat([w.codes for w in ws], 0)
+        assert QWeight.can_cat(ws)
         zp = None if ws[0].zp is None else torch.cat([w.zp for w in ws], 0)
         bias = None if ws[0].bias is None else torch.cat([w.bias for w in ws], 0)
+        delta = torch.cat([w.delta for w in ws], 0)
+        if any(w.codes is None for w in ws):             # packed-only 4-bit layers: the packing is row-wise, rows concatenate
+            return QWeight(None, delta, zp, bias, ws[0].n_bits, torch.cat([w.packed for w in ws], 0), K=ws[0].K)
+        codes = torch.cat([w.codes for w in ws], 0)
         packed = b200q.pack_w4(codes) if ws[0].n_bits <= 4 else None
-        return QWeight(codes, torch.cat([w.delta for w in ws], 0), zp, bias, ws[0].n_bits, packed)
+        return QWeight(codes, delta, zp, bias, ws[0].n_bits, packed)
+
+    @staticmethod
+    def can_cat(ws):
+        """plain quantized layers reading the same activation codes: same bit-width / K, no per-layer pre-transform,
+        zero points and biases present in all or in none"""
+        return (all(isinstance(w, QWeight) and w.pre is None and w.n_bits == ws[0].n_bits and w.K == ws[0].K for w in ws)
+                and len({w.zp is None for w in ws}) == 1 and len({w.bias is None for w in ws}) == 1)
 
     @staticmethod
     def random(N, K, n_bits=8, device="cuda", generator=None, with_zp=True):
@@ -113,12 +128,94 @@ class QWeight:
         return (self.packed.numel() if self.packed is not None else self.codes.numel())
 
 
-def qlinear(qa, da, rowsum, w: QWeight, out_dtype=torch.bfloat16, epilogue=b200q.EPI_NONE, residual=None, gate=None):
+class FPWeight:
+    """A linear the quant config keeps in floating point (`remain_fp_regex`, quant_model.py:57-60, or mixed-precision
+    index 0, :90-92; the shipped YAML keeps o / ffn / cross_attn FP, quant_configs/config.yaml:9): bf16 weight, library
+    GEMM - what the reference's nn.Linear computes under the pipeline's bf16 autocast (text2video.py:213)."""
+
+    def __init__(self, weight, bias=None):
+        self.weight = weight.detach().to(device="cuda", dtype=torch.bfloat16).contiguous()
+        self.bias = None if bias is None else bias.detach().to(device="cuda", dtype=torch.bfloat16).contiguous()
+        self.N, self.K = self.weight.shape
+        self.pre = None
+
+
+class DenseRotation:
+    """Activation transform with an arbitrary orthogonal matrix (a rotation that is not diag(s).H_n/sqrt(n) of this
+    package's construction, or a size the fused kernel does not serve): (x * mask) @ R in fp32, then the row quantizer."""
+
+    def __init__(self, R, mask=None, device="cuda"):
+        self.R = None if R is None else R.detach().to(device=device, dtype=torch.float32).contiguous()
+        self.mask = None if mask is None else mask.detach().to(device=device, dtype=torch.float32).reshape(1, -1)
+
+    def quantize(self, x2d, n_bits=8, want_rowsum=True):
+        y = x2d.float()
+        if self.mask is not None:
+            y = y * self.mask
+        if self.R is not None:
+            y = y @ self.R
+        q, d, _, rs = b200q.quant_rows(y, n_bits, True, True, want_rowsum=want_rowsum)
+        return q, d, rs
+
+
+def act_transform_of(layer, device):
+    """Activation pre-transform of a qdiff layer (SQ / QuaRot / ViDiT-Q variants) for the runtime, or None (plain)."""
+    plan = layer._act_plan(device) if hasattr(layer, "_act_plan") else None
+    if plan is not None:
+        return plan
+    mask = getattr(layer, "channel_mask", None)
+    R = getattr(layer, "rotation_matrix", None)
+    if mask is None and R is None:
+        return None
+    return DenseRotation(R, mask, device)
+
+
+class Act:
+    """One activation tensor as the linears consuming it need it: `fp` (fp32 / bf16 [rows, C]) for FP layers and layers
+    with their own pre-transform, plain per-token int8 codes (qa, delta, rowsum) for the plain quantized layers.  The
+    producing kernel fills in what it has; the rest is derived on first use."""
+
+    def __init__(self, fp=None, codes=None, a_bits=8):
+        self.fp, self.codes, self.a_bits, self._bf16 = fp, codes, a_bits, None
+
+    def q(self):
+        if self.codes is None:
+            qa, da, _, rs = b200q.quant_rows(self.fp, self.a_bits, True, True)
+            self.codes = (qa, da, rs)
+        return self.codes
+
+    def bf16(self):
+        if self._bf16 is None:
+            self._bf16 = self.fp if self.fp.dtype == torch.bfloat16 else self.fp.to(torch.bfloat16)
+        return self._bf16
+
+
+def qlinear(qa, da, rowsum, w: QWeight, out_dtype=torch.bfloat16, epilogue=b200q.EPI_NONE, residual=None, gate=None, out=None):
     if w.packed is not None:
         return b200q.gemm_w4a8(qa, w.packed, w.K, da, w.delta, w.zp, rowsum, w.bias, out_dtype=out_dtype,
-                               epilogue=epilogue, residual=residual, gate=gate)
+                               epilogue=epilogue, residual=residual, gate=gate, out=out)
     return b200q.gemm_w8a8(qa, w.codes, da, w.delta, w.zp, rowsum, w.bias, out_dtype=out_dtype, epilogue=epilogue,
-                           residual=residual, gate=gate)
+                           residual=residual, gate=gate, out=out)
+
+
+def apply_linear(w, act: Act, epilogue=b200q.EPI_NONE, residual=None, gate=None, out=None):
+    """One linear of the block on the activation `act`: integer GEMM (plain codes or the layer's own smooth/rotate
+    transform fused into its quantizer) or the bf16 library GEMM for an FP layer, with the same epilogue semantics."""
+    if isinstance(w, FPWeight):
+        y = F.linear(act.bf16(), w.weight, w.bias)
+        if epilogue == b200q.EPI_GELU_TANH:
+            y = F.gelu(y, approximate="tanh")
+        if epilogue == b200q.EPI_GATE_RESIDUAL:
+            return b200q.gate_residual(y, residual, gate)
+        if out is not None:
+            out.copy_(y)
+            return out
+        return y
+    if w.pre is not None:
+        qa, da, rs = w.pre.quantize(act.fp, act.a_bits)
+    else:
+        qa, da, rs = act.q()
+    return qlinear(qa, da, rs, w, epilogue=epilogue, residual=residual, gate=gate, out=out)
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -185,20 +282,59 @@ def sdpa(q, k, v, num_heads):
     return o.squeeze(0).permute(1, 0, 2).reshape(Lq, num_heads * hd)
 
 
+# bf16 attention core of the step: "b200q" = this repo's tcgen05 flash-attention kernel (b200q.attn_bf16), "library" =
+# torch SDPA (cuDNN / flash-attn, what the reference calls, wan/modules/attention.py:94-127).
+ATTENTION_CORE = "library"
+
+
+def set_attention_core(name):
+    global ATTENTION_CORE
+    if name not in ("library", "b200q"):
+        raise ValueError(name)
+    ATTENTION_CORE = name
+
+
+def attention_bf16(q, k, v, num_heads):
+    """bf16 attention core, q [Lq, H*hd], k,v [Lk, H*hd] (any row pitch) -> [Lq, H*hd] bf16."""
+    if ATTENTION_CORE == "b200q":
+        return b200q.attn_bf16(q, k, v, num_heads)
+    return sdpa(q, k, v, num_heads)
+
+
 # ------------------------------------------------------------------------------------------------------------
 # one block
 # ------------------------------------------------------------------------------------------------------------
+LINEARS = ("self_attn.q", "self_attn.k", "self_attn.v", "self_attn.o", "cross_attn.q", "cross_attn.k", "cross_attn.v",
+           "cross_attn.o", "ffn.0", "ffn.2")
+
+
 class WanBlockQ:
-    """Integer runtime of WanAttentionBlock.forward (wan/modules/model.py:293-370)."""
+    """Integer runtime of WanAttentionBlock.forward (wan/modules/model.py:293-370).
+
+    Each of the ten linears is a QWeight (integer GEMM; optionally with its own smooth-scale / Hadamard-rotation
+    activation transform, `QWeight.pre`) or an FPWeight (layer kept in floating point by the quant config).  Plain
+    quantized layers that read the same activation (q|k|v, cross k|v) are concatenated along N and served by ONE GEMM
+    on shared activation codes - the fast path of the all-W8A8 configs; any other mix runs layer by layer."""
 
     def __init__(self, cfg: WanConfig, w: dict, a_bits=8, attn_quant=False):
-        """attn_quant: 8-bit Q.K^T / P.V attention (quant_config `attn.qk`, `attn.v`, `attn.attn_map`, SURVEY §8 a-8 /
-        BASELINE configs[4]) through the fused int8 kernel instead of the library bf16 flash attention."""
+        """w: the ten LINEARS (or the pre-concatenated "self_attn.qkv" / "cross_attn.kv") plus norm weights and
+        `modulation`.  attn_quant: 8-bit Q.K^T / P.V attention (quant_config `attn.qk`, `attn.v`, `attn.attn_map`,
+        SURVEY §8 a-8 / BASELINE configs[4]) through the fused int8 kernel instead of bf16 flash attention."""
         self.cfg, self.a_bits, self.attn_quant = cfg, a_bits, attn_quant
-        self.w_qkv = w["self_attn.qkv"]
-        self.w_o = w["self_attn.o"]
-        self.w_cq, self.w_ckv, self.w_co = w["cross_attn.q"], w["cross_attn.kv"], w["cross_attn.o"]
-        self.w_f0, self.w_f2 = w["ffn.0"], w["ffn.2"]
+        lin = {k: w[k] for k in LINEARS if k in w}
+        qkv = ("self_attn.q", "self_attn.k", "self_attn.v")
+        ckv = ("cross_attn.k", "cross_attn.v")
+        self.w_qkv = w.get("self_attn.qkv")
+        if self.w_qkv is None and QWeight.can_cat([lin[k] for k in qkv]):
+            self.w_qkv = QWeight.cat([lin[k] for k in qkv])
+        self.w_ckv = w.get("cross_attn.kv")
+        if self.w_ckv is None and QWeight.can_cat([lin[k] for k in ckv]):
+            self.w_ckv = QWeight.cat([lin[k] for k in ckv])
+        # members only needed when the group is not served by one GEMM (drop the duplicates of concatenated weights)
+        self.lin = {k: v for k, v in lin.items()
+                    if not ((k in qkv and self.w_qkv is not None) or (k in ckv and self.w_ckv is not None))}
+        self.w_o, self.w_cq, self.w_co = lin["self_attn.o"], lin["cross_attn.q"], lin["cross_attn.o"]
+        self.w_f0, self.w_f2 = lin["ffn.0"], lin["ffn.2"]
         self.norm_q, self.norm_k = w["self_attn.norm_q.weight"], w["self_attn.norm_k.weight"]
         self.cnorm_q, self.cnorm_k = w["cross_attn.norm_q.weight"], w["cross_attn.norm_k.weight"]
         self.norm3_w, self.norm3_b = w.get("norm3.weight"), w.get("norm3.bias")
@@ -206,21 +342,18 @@ class WanBlockQ:
         self.attention_fn = None          # set by the sequence-parallel wrapper / int8 attention
 
     @staticmethod
-    def from_fp_params(cfg: WanConfig, p: dict, w_bits=8, w_sym=False, w_bits_by_layer=None, attn_quant=False):
-        """p: fp32 tensors keyed like oracle.fakequant_oracle.make_block_params (same names as the module tree)."""
+    def from_fp_params(cfg: WanConfig, p: dict, w_bits=8, w_sym=False, w_bits_by_layer=None, attn_quant=False,
+                       fp_layers=()):
+        """p: fp32 tensors keyed like oracle.fakequant_oracle.make_block_params (same names as the module tree).
+        fp_layers: names of linears to keep in floating point."""
         w_bits_by_layer = w_bits_by_layer or {}
 
         def q(name):
+            if name in fp_layers:
+                return FPWeight(p[name + ".weight"], p.get(name + ".bias"))
             return QWeight.from_fp(p[name + ".weight"], p.get(name + ".bias"), w_bits_by_layer.get(name, w_bits), w_sym)
 
-        w = {
-            "self_attn.qkv": QWeight.cat([q("self_attn.q"), q("self_attn.k"), q("self_attn.v")]),
-            "self_attn.o": q("self_attn.o"),
-            "cross_attn.q": q("cross_attn.q"),
-            "cross_attn.kv": QWeight.cat([q("cross_attn.k"), q("cross_attn.v")]),
-            "cross_attn.o": q("cross_attn.o"),
-            "ffn.0": q("ffn.0"), "ffn.2": q("ffn.2"),
-        }
+        w = {name: q(name) for name in LINEARS}
         for k in ("self_attn.norm_q.weight", "self_attn.norm_k.weight", "cross_attn.norm_q.weight",
                   "cross_attn.norm_k.weight", "norm3.weight", "norm3.bias", "modulation"):
             if k in p:
@@ -247,68 +380,110 @@ class WanBlockQ:
             w[k] = torch.ones(D, device=dev)
         return WanBlockQ(cfg, w, attn_quant=attn_quant)
 
-    # ---- forward ------------------------------------------------------------------------------------------
+    # ---- building blocks ----------------------------------------------------------------------------------
     def _default_attention(self, q, k, v):
-        return sdpa(q, k, v, self.cfg.num_heads)
+        return attention_bf16(q, k, v, self.cfg.num_heads)
+
+    def _ln_act(self, x, consumers, **ln):
+        """LayerNorm (+ affine / adaLN modulate) of the fp32 residual stream, emitted in the forms `consumers` need:
+        int8 codes straight from the fused kernel for plain quantized layers, the fp32 activations for FP layers and
+        layers with their own pre-transform."""
+        need_codes = any(isinstance(w, QWeight) and w.pre is None for w in consumers)
+        need_fp = any(isinstance(w, FPWeight) or w.pre is not None for w in consumers)
+        qa, da, rs, y = b200q.ln_mod_quant(x, self.cfg.eps, n_bits=self.a_bits, quant=need_codes,
+                                           y_dtype=torch.float32 if need_fp else None, **ln)
+        return Act(fp=y, codes=(qa, da, rs) if need_codes else None, a_bits=self.a_bits)
+
+    def _project(self, act, fused, names):
+        """act -> [rows, sum N] bf16: one GEMM on the concatenated weights, or member by member into column slices."""
+        if fused is not None:
+            return qlinear(*act.q(), fused)
+        ws = [self.lin[n] for n in names]
+        rows = act.fp.shape[0] if act.fp is not None else act.codes[0].shape[0]
+        out = torch.empty((rows, sum(w.N for w in ws)), dtype=torch.bfloat16, device=self.modulation.device)
+        off = 0
+        for w in ws:
+            apply_linear(w, act, out=out[:, off:off + w.N])
+            off += w.N
+        return out
+
+    def _group(self, fused, names):
+        return [fused] if fused is not None else [self.lin[n] for n in names]
 
     def context_kv(self, context):
         """cross-attention K,V of the (rank-replicated) text context [T, D] — token-local, once per block."""
         cfg = self.cfg
-        qc, dc, _, rc = b200q.quant_rows(context, self.a_bits, True, True)
-        kv = qlinear(qc, dc, rc, self.w_ckv)                                   # [T, 2D] bf16
+        kv = self._project(Act(fp=context, a_bits=self.a_bits), self.w_ckv, ("cross_attn.k", "cross_attn.v"))   # [T, 2D] bf16
         k = rmsnorm_rope(kv[:, :cfg.dim], self.cnorm_k, cfg.eps)
         return k, kv[:, cfg.dim:]
 
     def context_kv_i8(self, context):
         """int8 operands of the cross-attention keys/values: (kq, dk, vt, dv)."""
         cfg = self.cfg
-        qc, dc, _, rc = b200q.quant_rows(context, self.a_bits, True, True)
-        kv = qlinear(qc, dc, rc, self.w_ckv)
+        kv = self._project(Act(fp=context, a_bits=self.a_bits), self.w_ckv, ("cross_attn.k", "cross_attn.v"))
         kq, dk, _ = b200q.rmsnorm_rope_quant(kv[:, :cfg.dim], self.cnorm_k, cfg.eps, None, None, cfg.head_dim)
         vt, dv = b200q.quant_vt(kv[:, cfg.dim:], 8)
         return kq, dk, vt, dv
 
-    def forward(self, x, e0, context, cos, sin, attention=None):
-        """x [L, D] fp32 (updated in place and returned), e0 [6, D] fp32, context [T, D] fp32/bf16."""
+    # ---- forward ------------------------------------------------------------------------------------------
+    def forward(self, x, e0, context, cos, sin, attention=None, batch=1):
+        """x [B*L, D] fp32 (updated in place and returned), e0 [6, D] fp32, context [B*T, D] fp32/bf16.
+        batch = B > 1: the cond / uncond branches of classifier-free guidance (text2video.py:254-257 runs them as two
+        serial forwards) stacked along the rows; every token-local stage then runs once on B*L rows and only the two
+        attentions are evaluated per branch.  cos/sin cover the B*L rows."""
         cfg = self.cfg
         D, H = cfg.dim, cfg.num_heads
         e = self.modulation + e0                                                # model.py:322-324 (fp32)
         local_attention = attention is None and self.attention_fn is None       # no sequence-parallel exchange in the way
         attention = attention or self.attention_fn or self._default_attention
+        B = int(batch)
+        L = x.shape[0] // B
+        T = context.shape[0] // B
+        rows = lambda t, b, n: t[b * n:(b + 1) * n]
 
         # ---- self attention (model.py:327-337 with xdit_context_parallel.py:163-165 semantics) ----
-        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, shift=e[0], scale=e[1], n_bits=self.a_bits)
-        qkv = qlinear(qa, da, rs, self.w_qkv)                                   # [L, 3D] bf16
+        qkv_names = ("self_attn.q", "self_attn.k", "self_attn.v")
+        act = self._ln_act(x, self._group(self.w_qkv, qkv_names), shift=e[0], scale=e[1])
+        qkv = self._project(act, self.w_qkv, qkv_names)                         # [B*L, 3D] bf16
         if self.attn_quant and local_attention:
             # token-local int8 path: Q/K codes straight out of the RMSNorm+RoPE kernel, V^T codes, fused attention
             qq, dq, _ = b200q.rmsnorm_rope_quant(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, cfg.head_dim)
             kq, dk, _ = b200q.rmsnorm_rope_quant(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, cfg.head_dim)
-            vt, dv = b200q.quant_vt(qkv[:, 2 * D:], 8)
-            a = b200q.attn_i8(qq, dq, kq, dk, vt, dv, H)
+            a = torch.empty((B * L, D), dtype=torch.bfloat16, device=x.device) if B > 1 else None
+            for b in range(B):
+                vt, dv = b200q.quant_vt(rows(qkv, b, L)[:, 2 * D:], 8)
+                o = b200q.attn_i8(rows(qq, b, L), rows(dq, b, L), rows(kq, b, L), rows(dk, b, L), vt, dv, H,
+                                  out=None if a is None else rows(a, b, L))
+                a = o if a is None else a
         else:
             q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H)
             k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H)
-            a = attention(q, k, qkv[:, 2 * D:])
-        qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
-        qlinear(qa, da, rs, self.w_o, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[2])
+            v = qkv[:, 2 * D:]
+            a = attention(q, k, v) if B == 1 else torch.cat([attention(rows(q, b, L), rows(k, b, L), rows(v, b, L))
+                                                             for b in range(B)], 0)
+        apply_linear(self.w_o, Act(fp=a, a_bits=self.a_bits), epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[2])
 
         # ---- cross attention (model.py:180-200, 351-353) ----
-        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, ln_w=self.norm3_w, ln_b=self.norm3_b, n_bits=self.a_bits)
+        act = self._ln_act(x, [self.w_cq], ln_w=self.norm3_w, ln_b=self.norm3_b)
+        cq = apply_linear(self.w_cq, act)
         if self.attn_quant:
-            qq, dq, _ = b200q.rmsnorm_rope_quant(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps, None, None, cfg.head_dim)
-            a = b200q.attn_i8(qq, dq, *self.context_kv_i8(context), H)
+            qq, dq, _ = b200q.rmsnorm_rope_quant(cq, self.cnorm_q, cfg.eps, None, None, cfg.head_dim)
+            a = torch.empty((B * L, D), dtype=torch.bfloat16, device=x.device) if B > 1 else None
+            for b in range(B):
+                o = b200q.attn_i8(rows(qq, b, L), rows(dq, b, L), *self.context_kv_i8(rows(context, b, T)), H,
+                                  out=None if a is None else rows(a, b, L))
+                a = o if a is None else a
         else:
-            q = rmsnorm_rope(qlinear(qa, da, rs, self.w_cq), self.cnorm_q, cfg.eps)
+            q = rmsnorm_rope(cq, self.cnorm_q, cfg.eps)
             ck, cv = self.context_kv(context)
-            a = sdpa(q, ck, cv, H)
-        qa, da, _, rs = b200q.quant_rows(a, self.a_bits, True, True)
-        qlinear(qa, da, rs, self.w_co, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=None)
+            a = attention_bf16(q, ck, cv, H) if B == 1 else torch.cat(
+                [attention_bf16(rows(q, b, L), rows(ck, b, T), rows(cv, b, T), H) for b in range(B)], 0)
+        apply_linear(self.w_co, Act(fp=a, a_bits=self.a_bits), epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=None)
 
         # ---- ffn (model.py:286-288, 359-362) ----
-        qa, da, rs, _ = b200q.ln_mod_quant(x, cfg.eps, shift=e[3], scale=e[4], n_bits=self.a_bits)
-        h = qlinear(qa, da, rs, self.w_f0, epilogue=b200q.EPI_GELU_TANH)       # [L, F] bf16
-        qa, da, _, rs = b200q.quant_rows(h, self.a_bits, True, True)
-        qlinear(qa, da, rs, self.w_f2, epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[5])
+        act = self._ln_act(x, [self.w_f0], shift=e[3], scale=e[4])
+        h = apply_linear(self.w_f0, act, epilogue=b200q.EPI_GELU_TANH)         # [B*L, F] bf16
+        apply_linear(self.w_f2, Act(fp=h, a_bits=self.a_bits), epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[5])
         return x
 
     def gemm_ops(self, L, T):
@@ -362,8 +537,38 @@ class WanDiTQ:
         }
         return WanDiTQ(cfg, blocks, fp, sp)
 
+    @staticmethod
+    def from_fp_state_dict(cfg: WanConfig, sd: dict, w_bits=8, w_sym=False, remain_fp_regex=None, w_bits_by_layer=None,
+                           attn_quant=False, sp=None):
+        """Quantize an FP WanModel state dict (parameter names of wan/modules/model.py:480-540) on the device: what
+        `quant_layer_refactor` + `quantize_and_save_weight` + `hardware_forward_refactor` do in three steps
+        (quant_wanx.py:91-99, 137-228), for plain QuantizedLinear layers.  `remain_fp_regex` is matched against the
+        dotted layer names exactly as quant_model.py:57-60 does; matching block linears stay FP."""
+        import re
+        fp_re = re.compile(remain_fp_regex) if remain_fp_regex else None
+        blocks = []
+        for i in range(cfg.num_layers):
+            pre = f"blocks.{i}."
+            p = {k[len(pre):]: v for k, v in sd.items() if k.startswith(pre)}
+            fp_layers = tuple(n for n in LINEARS if fp_re is not None and fp_re.search(pre + n))
+            blocks.append(WanBlockQ.from_fp_params(cfg, p, w_bits, w_sym, w_bits_by_layer, attn_quant, fp_layers))
+        bf = lambda k: sd[k].detach().to(device="cuda", dtype=torch.bfloat16).contiguous()
+        pdim = cfg.in_dim * math.prod(cfg.patch_size)
+        fp = {
+            "patch": (bf("patch_embedding.weight").reshape(cfg.dim, pdim), bf("patch_embedding.bias")),
+            "text0": (bf("text_embedding.0.weight"), bf("text_embedding.0.bias")),
+            "text2": (bf("text_embedding.2.weight"), bf("text_embedding.2.bias")),
+            "time0": (bf("time_embedding.0.weight"), bf("time_embedding.0.bias")),
+            "time2": (bf("time_embedding.2.weight"), bf("time_embedding.2.bias")),
+            "timeproj": (bf("time_projection.1.weight"), bf("time_projection.1.bias")),
+            "head": (bf("head.head.weight"), bf("head.head.bias")),
+            "head_mod": sd["head.modulation"].detach().float().cuda().reshape(2, cfg.dim).contiguous(),
+        }
+        return WanDiTQ(cfg, blocks, fp, sp)
+
     def embed(self, latent, t, context):
-        """patch embedding (Conv3d with stride == kernel == a linear on patches), time MLP (fp32), text MLP."""
+        """patch embedding (Conv3d with stride == kernel == a linear on patches), time MLP (fp32), text MLP.
+        context [T, text_dim] or a list / stack of B of them -> ctx [B*text_len, D]."""
         cfg, fp = self.cfg, self.fp
         C, Fr, Hh, Ww = latent.shape
         pt, ph, pw = cfg.patch_size
@@ -375,9 +580,11 @@ class WanDiTQ:
         e = F.linear(F.silu(F.linear(te, fp["time0"][0].float(), fp["time0"][1].float())), fp["time2"][0].float(),
                      fp["time2"][1].float())
         e0 = F.linear(F.silu(e), fp["timeproj"][0].float(), fp["timeproj"][1].float()).view(6, cfg.dim)
-        ctx = torch.zeros(cfg.text_len, cfg.text_dim, device=x.device, dtype=torch.bfloat16)
-        ctx[:context.shape[0]] = context.to(torch.bfloat16)
-        ctx = F.linear(F.gelu(F.linear(ctx, *fp["text0"]), approximate="tanh"), *fp["text2"])
+        contexts = [context] if (torch.is_tensor(context) and context.dim() == 2) else list(context)
+        ctx = torch.zeros(len(contexts), cfg.text_len, cfg.text_dim, device=x.device, dtype=torch.bfloat16)
+        for b, c in enumerate(contexts):
+            ctx[b, :c.shape[0]] = c.to(torch.bfloat16)
+        ctx = F.linear(F.gelu(F.linear(ctx.view(-1, cfg.text_dim), *fp["text0"]), approximate="tanh"), *fp["text2"])
         return x, e, e0, ctx, grid
 
     def head(self, x, e):
@@ -395,27 +602,40 @@ class WanDiTQ:
 
     @torch.no_grad()
     def forward(self, latent, t, context):
-        """latent [C, F, H, W], t [1], context [T<=512, text_dim] -> denoised latent [C, F, H, W] fp32."""
+        """latent [C, F, H, W], t [1], context [T<=512, text_dim] -> denoised latent [C, F, H, W] fp32.
+        A list (or [B, T, text_dim] stack) of contexts runs the B classifier-free-guidance branches of the same latent
+        and timestep as ONE batched step (rows stacked; the reference runs them as serial forwards,
+        text2video.py:254-257) and returns [B, C, F, H, W]."""
+        batched = not (torch.is_tensor(context) and context.dim() == 2)
         x, e, e0, ctx, grid = self.embed(latent, t, context)
+        B = ctx.shape[0] // self.cfg.text_len
         L = x.shape[0]
         sp = self.sp
-        if sp is not None and sp.world_size > 1:
+        sharded = sp is not None and sp.world_size > 1
+        if sharded:
             x, off, Lr = sp.shard_tokens(x)                        # xdit_context_parallel.py:131-133
         else:
             off, Lr = 0, L
         cos, sin = rope_table(self.cfg.head_dim, grid, x.device, off, Lr)
-        if sp is not None and sp.world_size > 1 and cos.shape[0] < x.shape[0]:   # padded tail tokens: identity rotation
+        if sharded and cos.shape[0] < x.shape[0]:                  # padded tail tokens: identity rotation
             pad = x.shape[0] - cos.shape[0]
             cos = torch.cat([cos, torch.ones(pad, cos.shape[1], device=cos.device)])
             sin = torch.cat([sin, torch.zeros(pad, sin.shape[1], device=sin.device)])
-        attn = (lambda q, k, v: sp.attention(q, k, v, self.cfg.num_heads)) if (sp is not None and sp.world_size > 1) else None
+        attn = (lambda q, k, v: sp.attention(q, k, v, self.cfg.num_heads)) if sharded else None
+        if B > 1:
+            x, cos, sin = x.repeat(B, 1), cos.repeat(B, 1), sin.repeat(B, 1)
         x = x.contiguous()
         for blk in self.blocks:
-            blk.forward(x, e0, ctx, cos, sin, attention=attn)
+            blk.forward(x, e0, ctx, cos, sin, attention=attn, batch=B)
         y = self.head(x, e[0])
-        if sp is not None and sp.world_size > 1:
-            y = sp.gather_tokens(y, L)                             # xdit_context_parallel.py:142
-        return self.unpatchify(y, grid)
+        n = y.shape[0] // B
+        outs = []
+        for b in range(B):
+            yb = y[b * n:(b + 1) * n]
+            if sharded:
+                yb = sp.gather_tokens(yb, L)                       # xdit_context_parallel.py:142
+            outs.append(self.unpatchify(yb, grid))
+        return torch.stack(outs, 0) if batched else outs[0]
 
     def gemm_ops(self, L):
         return sum(b.gemm_ops(L, self.cfg.text_len) for b in self.blocks)

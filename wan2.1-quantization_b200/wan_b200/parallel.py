@@ -113,7 +113,7 @@ class SequenceParallel:
         """q,k,v: this rank's tokens, all heads, [Lr, H*hd] -> attention output [Lr, H*hd] for the same tokens."""
         from . import model as M                       # late import: model imports nothing from here
         P = self.world_size
-        core = self.attention_core or M.sdpa
+        core = self.attention_core or M.attention_bf16
         if P == 1:
             return core(q, k, v, num_heads)
         Lr, D = q.shape
