@@ -100,7 +100,7 @@ def test_had_quant_rows_gpu(dev, n, dtype):
     qo, do, _ = O.quant_rows(y, 8, True, True)
     assert torch.equal(q.cpu().float(), qo) and torch.equal(d.cpu(), do.flatten())
     assert torch.equal(rs.cpu(), qo.to(torch.int32).sum(dim=1).to(torch.int32))
-    assert float(d[3]) == 1e-6 and int(q[3].abs().max()) == 0
+    assert float(d[3]) == float(torch.tensor(1e-6, dtype=torch.float32)) and int(q[3].abs().max()) == 0
 
 
 @pytest.mark.gpu

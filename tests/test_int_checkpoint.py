@@ -303,4 +303,4 @@ def test_viditq_shipped_config_hardware_forward_vs_oracle_gpu(dev, tmp_path):
         for n in ("self_attn.q", "self_attn.k", "self_attn.v"):
             bq.lin[n].pre = None
     bad = m([lat.to(dev)], t.to(dev), [ctx.to(dev)], 48)[0].cpu().double().flatten()
-    assert float((bad @ b) / (bad.norm() * b.norm())) < 0.99
+    assert float((bad @ b) / (bad.norm() * b.norm())) < 0.995 < cos

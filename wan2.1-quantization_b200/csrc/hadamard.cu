@@ -62,11 +62,11 @@ __device__ __forceinline__ void fwht_segment(float* seg, int lane) {
   }
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const bool upper = (lane & o) != 0;
+    const float sgn = (lane & o) ? -1.f : 1.f;        // upper half of the butterfly: other - v, lower: v + other
 #pragma unroll
     for (int i = 0; i < E; ++i) {
       const float other = __shfl_xor_sync(0xffffffffu, v[i], o);
-      v[i] = upper ? other - v[i] : v[i] + other;
+      v[i] = fmaf(v[i], sgn, other);
     }
   }
   if constexpr (E >= 4) {
@@ -95,14 +95,16 @@ __device__ __forceinline__ void kblock_group(float* base, int W, int K, const fl
   }
   for (int i = 0; i < K; ++i) {
     uint64_t a01 = 0, a23 = 0;                      // bit pattern of (0.f, 0.f)
-    const float2* hrow = s_h2 + i * K;
+    const float4* hrow = reinterpret_cast<const float4*>(s_h2 + i * K);   // K is even: 16-byte aligned rows
 #pragma unroll
-    for (int j = 0; j < KM; ++j) {
+    for (int j = 0; j < KM; j += 2) {
       if (j < K) {
-        const float2 hh = hrow[j];                  // (h, h): broadcast LDS.64
-        const uint64_t h2 = pack_f32x2(hh.x, hh.y);
-        a01 = fma_f32x2(h2, y01[j], a01);
-        a23 = fma_f32x2(h2, y23[j], a23);
+        const float4 hh = hrow[j >> 1];             // (h_j, h_j, h_j+1, h_j+1): one broadcast LDS.128
+        const uint64_t h2a = pack_f32x2(hh.x, hh.y), h2b = pack_f32x2(hh.z, hh.w);
+        a01 = fma_f32x2(h2a, y01[j], a01);
+        a23 = fma_f32x2(h2a, y23[j], a23);
+        a01 = fma_f32x2(h2b, y01[j + 1], a01);
+        a23 = fma_f32x2(h2b, y23[j + 1], a23);
       }
     }
     float o0, o1, o2, o3;
@@ -128,27 +130,36 @@ __global__ void __launch_bounds__(HAD_THREADS, KM <= 12 ? 3 : (KM <= 20 ? 2 : 1)
   if (K > 1) for (int i = tid; i < K * K; i += HAD_THREADS) { const float h = a.hadK[i]; s_h2[i] = make_float2(h, h); }
   if (tid < R) { s_amax[tid] = 0; s_sum[tid] = 0; }
 
-  // ---- phase 1: load, * colscale -> smem ----
+  // ---- phase 1: load, * colscale -> smem (LD loads in flight per thread before the first use) ----
   const int kv = n / N;
-  for (int f = tid; f < R * kv; f += HAD_THREADS) {
-    const int r = f / kv, v = f - r * kv;
-    const int64_t row = row0 + r;
-    float x[N];
-    if (row < a.rows) {
-      VT::unpack(ldg_stream16(reinterpret_cast<const T*>(a.x) + row * a.ldx + (int64_t)v * N), x);
-    } else {
+  constexpr int LD = 4;
+  for (int f0 = tid; f0 < R * kv; f0 += LD * HAD_THREADS) {
+    uint4 raw[LD];
 #pragma unroll
-      for (int i = 0; i < N; ++i) x[i] = 0.f;
+    for (int u = 0; u < LD; ++u) {
+      const int f = f0 + u * HAD_THREADS;
+      const int r = f / kv, v = f - r * kv;
+      const int64_t row = row0 + r;
+      raw[u] = (f < R * kv && row < a.rows) ? ldg_stream16(reinterpret_cast<const T*>(a.x) + row * a.ldx + (int64_t)v * N)
+                                             : make_uint4(0, 0, 0, 0);
     }
-    float* dst = buf + (size_t)r * n + v * N;
 #pragma unroll
-    for (int h = 0; h < N / 4; ++h) {
-      float4 o = make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
-      if (a.colscale != nullptr) {
-        const float4 c = __ldg(reinterpret_cast<const float4*>(a.colscale + v * N + 4 * h));
-        o.x *= c.x; o.y *= c.y; o.z *= c.z; o.w *= c.w;
+    for (int u = 0; u < LD; ++u) {
+      const int f = f0 + u * HAD_THREADS;
+      if (f >= R * kv) break;
+      const int r = f / kv, v = f - r * kv;
+      float x[N];
+      VT::unpack(raw[u], x);
+      float* dst = buf + (size_t)r * n + v * N;
+#pragma unroll
+      for (int h = 0; h < N / 4; ++h) {
+        float4 o = make_float4(x[4 * h], x[4 * h + 1], x[4 * h + 2], x[4 * h + 3]);
+        if (a.colscale != nullptr) {
+          const float4 c = __ldg(reinterpret_cast<const float4*>(a.colscale + v * N + 4 * h));
+          o.x *= c.x; o.y *= c.y; o.z *= c.z; o.w *= c.w;
+        }
+        *reinterpret_cast<float4*>(dst + 4 * h) = o;
       }
-      *reinterpret_cast<float4*>(dst + 4 * h) = o;
     }
   }
   __syncthreads();
@@ -179,45 +190,51 @@ __global__ void __launch_bounds__(HAD_THREADS, KM <= 12 ? 3 : (KM <= 20 ? 2 : 1)
     __syncthreads();
   }
 
-  // ---- phase 4: per-row abs-max (n % 128 == 0: the 32 float4 of a warp iteration lie in one row) ----
+  // ---- phases 4 + 5: per-row abs-max, then quantize + store.  A row is owned by WPR = 8 / R warps (R in {1,2,4,8}), so
+  // the reductions are thread-local sums plus one warp reduction and one shared-memory atomic per warp and row. ----
   const int n4 = n >> 2;
-  for (int f = tid; f < R * n4; f += HAD_THREADS) {
-    const float4 t = *reinterpret_cast<const float4*>(buf + (size_t)f * 4);
-    float m = fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w)));
+  const int WPR = (HAD_THREADS / 32) / R;             // warps per row
+  const int r = warp / WPR, part = warp - r * WPR;
+  const int64_t row = row0 + r;
+  const float4* rowp = reinterpret_cast<const float4*>(buf + (size_t)r * n);
+  {
+    float m = 0.f;
+    for (int f = part * 32 + lane; f < n4; f += WPR * 32) {
+      const float4 t = rowp[f];
+      m = fmaxf(m, fmaxf(fmaxf(fabsf(t.x), fabsf(t.y)), fmaxf(fabsf(t.z), fabsf(t.w))));
+    }
     m = warp_max(m);
-    if (lane == 0) atomicMax(&s_amax[f / n4], __float_as_int(m));
+    if (lane == 0) atomicMax(&s_amax[r], __float_as_int(m));
   }
   __syncthreads();
-
-  // ---- phase 5: quantize + store ----
-  for (int f = tid; f < R * n4; f += HAD_THREADS) {
-    const int r = f / n4, v = f - r * n4;
-    const int64_t row = row0 + r;
+  {
     float delta = __fdiv_rn(__int_as_float(s_amax[r]), a.n_levels);
     if (delta < 1.0e-6f) delta = 1.0e-6f;                                // base_quantizer.py:122-128
     const float rc = __frcp_rn(delta);
-    const float4 t = *reinterpret_cast<const float4*>(buf + (size_t)f * 4);
     const uint64_t r2 = pack_f32x2(rc, rc), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
-    uint32_t c0, c1, c2, c3;
-    unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.x, t.y), nd2, r2, magic2), c0, c1);
-    unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.z, t.w), nd2, r2, magic2), c2, c3);
-    const uint32_t packed = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
-    int sum = __dp4a((int)packed, 0x01010101, 0);
-    if (row < a.rows) {
-      stg_stream4(a.q + row * a.ldq + (int64_t)v * 4, packed);
-      if (a.y_out != nullptr) *reinterpret_cast<float4*>(a.y_out + row * a.ldy + (int64_t)v * 4) = t;
+    int sum = 0;
+    const bool row_ok = row < a.rows;
+    for (int f = part * 32 + lane; f < n4; f += WPR * 32) {
+      const float4 t = rowp[f];
+      uint32_t c0, c1, c2, c3;
+      unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.x, t.y), nd2, r2, magic2), c0, c1);
+      unpack_u32x2(div_rn_hoisted_rne2(pack_f32x2(t.z, t.w), nd2, r2, magic2), c2, c3);
+      const uint32_t packed = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+      sum = __dp4a((int)packed, 0x01010101, sum);
+      if (row_ok) {
+        stg_stream4(a.q + row * a.ldq + (int64_t)f * 4, packed);
+        if (a.y_out != nullptr) *reinterpret_cast<float4*>(a.y_out + row * a.ldy + (int64_t)f * 4) = t;
+      }
     }
     if (a.rowsum != nullptr) {
       sum = warp_sum(sum);
       if (lane == 0) atomicAdd(&s_sum[r], sum);
     }
+    if (part == 0 && lane == 0 && row_ok) a.delta[row] = delta;
   }
-  __syncthreads();
-  if (tid < R && row0 + tid < a.rows) {
-    float delta = __fdiv_rn(__int_as_float(s_amax[tid]), a.n_levels);
-    if (delta < 1.0e-6f) delta = 1.0e-6f;
-    a.delta[row0 + tid] = delta;
-    if (a.rowsum != nullptr) a.rowsum[row0 + tid] = s_sum[tid];
+  if (a.rowsum != nullptr) {
+    __syncthreads();
+    if (tid < R && row0 + tid < a.rows) a.rowsum[row0 + tid] = s_sum[tid];
   }
 }
 
@@ -227,9 +244,9 @@ static int launch_had_km(const HadArgs& a0, cudaStream_t st) {
   const int n = (int)a.cols;
   const int W = 1 << a.log2w;
   // rows per CTA: enough 4-column groups for 256 threads in the K-block phase, within ~96 KB of shared memory
-  int R = 8;
+  (void)W;
+  int R = 8;                                           // power of two <= 8: a row is owned by 8 / R warps
   while (R > 1 && (size_t)R * n * 4 > 98304) R >>= 1;
-  if (a.K > 1) while (R > 1 && R * (W / 4) > 2 * HAD_THREADS && (size_t)R * n * 4 > 49152) R >>= 1;
   a.R = R;
   const size_t smem = (size_t)R * n * 4 + (size_t)a.K * a.K * 8 + (size_t)R * 8 + 16;
   B200Q_REQUIRE(smem <= 232448, B200Q_ERR_UNSUPPORTED, "had_quant_rows: cols=%d does not fit in shared memory", n);
