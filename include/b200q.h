@@ -229,6 +229,18 @@ B200Q_API int b200q_had_quant_rows(const void* x, int x_dtype, int64_t rows, int
 B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, int64_t ldv, int n_bits,
                    float* absmax_ws, int8_t* vt, int64_t ldvt, float* delta, b200q_stream_t stream);
 
+/* b200q_attn_bf16: bf16 flash attention, head_dim = 128 - the attention core of the W8A8 step.  Replaces the reference's
+ * flash-attn call (examples/Wan2.1/wan/modules/attention.py:94-127: flash_attn_varlen_func(q, k, v, softmax_scale =
+ * head_dim^-0.5), no mask, no dropout; SDPA fallback :171-178): out = softmax(q.k^T * sm_scale) . v per head.
+ *   q bf16 [Lq, H*128] (ldq), k, v bf16 [Lk, H*128] (ldk, ldv): row pitches in elements, multiples of 8, 16-byte aligned
+ *   bases - column slices of a fused q|k|v GEMM output are fine.  out bf16 [Lq, H*128] (ldo).
+ *   lse_out (optional, fp32 [H, Lq]): log2(sum_j 2^(x_ij)), x = q.k^T * sm_scale * log2(e), for merging key splits.
+ *   Q.K^T and P.V run as tcgen05.mma.kind::f16 with fp32 accumulators in TMEM, P is handed to the second product through
+ *   tensor memory, V is consumed in its natural [keys, head_dim] layout; fp32 softmax statistics. */
+B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                    int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
+                    float* lse_out, b200q_stream_t stream);
+
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the
  *   [L*H, 128] view); dq/dk: their fp32 scales, element (token, head) at dq[token*dq_tok_stride + head*dq_head_stride];

@@ -39,16 +39,18 @@ def test_library_builds_and_exports_every_declared_symbol():
 
 
 def test_sass_is_blackwell_native():
-    """tcgen05.mma.kind::i8 -> UTCIMMA, TMA -> UTMALDG/UTMASTG, tcgen05.ld -> LDTM (B200_PROFILING.md)."""
+    """tcgen05.mma.kind::i8 -> UTCIMMA, kind::f16 -> UTCHMMA, TMA -> UTMALDG/UTMASTG, tcgen05.ld -> LDTM (B200_PROFILING.md)."""
     import shutil
     import subprocess
     import b200q
     if shutil.which("cuobjdump") is None or not os.path.exists(b200q.LIB_PATH):
         pytest.skip("cuobjdump or library missing")
     sass = subprocess.run(["cuobjdump", "-sass", b200q.LIB_PATH], capture_output=True, text=True).stdout
-    for mnemonic in ("UTCIMMA", "UTMALDG", "UTMASTG", "LDTM", "FFMA2"):
+    import re
+    for mnemonic in ("UTCIMMA", "UTCHMMA", "UTMALDG", "UTMASTG", "LDTM", "STTM", "FFMA2"):
         assert mnemonic in sass, mnemonic
-    assert "HMMA" not in sass and "IMMA.16" not in sass        # no legacy mma.sync path
+    # no legacy mma.sync path (UTCHMMA = tcgen05.mma.kind::f16 is the Blackwell one)
+    assert re.search(r"(?<!UTC)HMMA", sass) is None and "IMMA.16" not in sass
 
 
 def test_no_cpu_fallback():

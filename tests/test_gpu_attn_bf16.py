@@ -1,0 +1,106 @@
+"""-m gpu: the bf16 tcgen05 flash-attention kernel (include/b200q.h b200q_attn_bf16) against fp32 softmax attention on the
+same bf16 inputs = the reference's attention call (wan/modules/attention.py:94-127, SDPA fallback :171-178).
+Tolerance: max |err| <= 2e-2 * max|ref| and cosine >= 0.9999 (bf16 P and bf16 output; fp32 accumulation and statistics)."""
+import pytest
+import torch
+
+import b200q
+
+pytestmark = pytest.mark.gpu
+
+
+def _ref(q, k, v, H, scale=None):
+    Lq, D = q.shape
+    hd = D // H
+    scale = hd ** -0.5 if scale is None else scale
+    qh, kh, vh = (t.float().view(t.shape[0], H, hd).permute(1, 0, 2) for t in (q, k, v))
+    s = (qh @ kh.transpose(1, 2)) * scale
+    p = torch.softmax(s, dim=-1)
+    lse = torch.logsumexp(s, dim=-1) * 1.4426950408889634
+    return (p @ vh).permute(1, 0, 2).reshape(Lq, D), lse
+
+
+def _check(out, ref, tol=2e-2):
+    out, ref = out.float(), ref.float()
+    err = float((out - ref).abs().max() / ref.abs().max())
+    cos = float((out.double().flatten() @ ref.double().flatten()) / (out.double().norm() * ref.double().norm()))
+    assert err <= tol and cos >= 0.9999, (err, cos)
+
+
+@pytest.mark.parametrize("H,Lq,Lk", [(2, 256, 128), (2, 200, 300), (1, 1, 1), (3, 257, 129), (12, 1000, 517), (2, 512, 1024),
+                                     (1, 128, 4096), (4, 3000, 512), (2, 77, 2000)])
+def test_attn_bf16_matches_fp32_softmax(dev, H, Lq, Lk):
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + Lq + Lk)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g).to(torch.bfloat16) for n in (Lq, Lk, Lk))
+    out, lse = b200q.attn_bf16(q, k, v, H, want_lse=True)
+    ref, lse_ref = _ref(q, k, v, H)
+    _check(out, ref)
+    assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
+    assert torch.equal(out, b200q.attn_bf16(q, k, v, H))            # deterministic
+
+
+def test_attn_bf16_strided_operands_and_scale(dev):
+    """q, k, v as column slices of a fused q|k|v GEMM output (row pitch 3*D), a non-default softmax scale"""
+    H, L = 3, 700
+    D = H * 128
+    g = torch.Generator(device="cuda").manual_seed(7)
+    qkv = torch.randn(L, 3 * D, device=dev, generator=g).to(torch.bfloat16)
+    q, k, v = qkv[:, :D], qkv[:, D:2 * D], qkv[:, 2 * D:]
+    out = b200q.attn_bf16(q, k, v, H, sm_scale=0.05)
+    _check(out, _ref(q, k, v, H, 0.05)[0])
+
+
+def test_attn_bf16_growing_maxima_trigger_rescaling(dev):
+    """row maxima that keep growing along the keys (every block exceeds the reference maximum by more than 2^8) and large
+    magnitudes: exercises the lazy O / l rescale path in every block, within a block, and the -inf start"""
+    H, Lq, Lk = 2, 300, 1500
+    g = torch.Generator(device="cuda").manual_seed(11)
+    q = torch.randn(Lq, H * 128, device=dev, generator=g)
+    k = torch.randn(Lk, H * 128, device=dev, generator=g)
+    v = torch.randn(Lk, H * 128, device=dev, generator=g)
+    ramp = torch.linspace(0.2, 6.0, Lk, device=dev).view(-1, 1)
+    k = k * ramp                                                     # scores grow with the key index
+    k[700:716] *= 3                                                  # a jump inside a 128-key block (chunk-level bump)
+    q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    out = b200q.attn_bf16(q, k, v, H)
+    _check(out, _ref(q, k, v, H)[0], tol=3e-2)
+    # descending maxima: the first block fixes the reference, nothing rescales afterwards
+    out = b200q.attn_bf16(q, k.flip(0).contiguous(), v, H)
+    _check(out, _ref(q, k.flip(0), v, H)[0], tol=3e-2)
+
+
+def test_attn_bf16_many_items_persistent_schedule(dev):
+    """more (head, query-tile) items than SMs: every CTA walks several items, barriers wrap their phases many times"""
+    H, Lq, Lk = 12, 4096 + 100, 640
+    g = torch.Generator(device="cuda").manual_seed(3)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g).to(torch.bfloat16) for n in (Lq, Lk, Lk))
+    _check(b200q.attn_bf16(q, k, v, H), _ref(q, k, v, H)[0])
+
+
+def test_attn_bf16_rejects_bad_arguments(dev):
+    q = torch.randn(64, 256, device=dev).to(torch.bfloat16)
+    with pytest.raises(b200q.B200QError):
+        b200q.attn_bf16(q, q, q, 4)                                  # head_dim 64
+    with pytest.raises(b200q.B200QError):
+        b200q.attn_bf16(q.float(), q, q, 2)                          # not bf16
+    with pytest.raises(b200q.B200QError):
+        b200q.attn_bf16(q, q[:, :128], q, 2)                         # shape mismatch
+
+
+def test_block_with_own_attention_core_matches_library_core(dev):
+    """the DiT block with ATTENTION_CORE = b200q vs library SDPA: same function, bf16-level agreement"""
+    from wan_b200 import model as M
+    cfg = M.WanConfig(dim=256, ffn_dim=512, num_heads=2, num_layers=2, text_dim=64, freq_dim=64)
+    dit = M.WanDiTQ.random(cfg, seed=0)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lat = torch.randn(16, 3, 8, 12, device=dev, generator=g)
+    ctx = torch.randn(20, 64, device=dev, generator=g)
+    t = torch.tensor([500.0], device=dev)
+    try:
+        M.set_attention_core("library")
+        y_lib = dit.forward(lat, t, ctx)
+        M.set_attention_core("b200q")
+        y_own = dit.forward(lat, t, ctx)
+    finally:
+        M.set_attention_core("library")
+    _check(y_own, y_lib, tol=3e-2)

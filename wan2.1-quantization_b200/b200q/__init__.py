@@ -63,6 +63,8 @@ _SIGNATURES = {
                               c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_int,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_attn_set_mode": (c_int, [c_int]),
+    "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
+                                c_void_p, c_int64, c_void_p, c_void_p]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "b200q_had_quant_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -382,6 +384,28 @@ def quant_vt(v, n_bits=8):
                                _ptr(delta), _stream())
     _check(rc, "b200q_quant_vt")
     return buf[:, :Lk], delta
+
+
+def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False):
+    """bf16 flash attention (include/b200q.h): q [Lq, H*128], k, v [Lk, H*128] bf16 (row-major, any row pitch that is a
+    multiple of 8 elements) -> bf16 [Lq, H*128]; want_lse=True also returns the fp32 [H, Lq] log2-sum-exp."""
+    for t, n in ((q, "q"), (k, "k"), (v, "v")):
+        _cuda(t, n)
+        if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
+            raise B200QError(f"attn_bf16: {n} must be a row-major 2-D bf16 tensor")
+    Lq, D = q.shape
+    Lk = k.shape[0]
+    H = int(num_heads)
+    if k.shape[1] != D or v.shape != k.shape or D % H != 0:
+        raise B200QError("attn_bf16: shape mismatch")
+    hd = D // H
+    sm_scale = hd ** -0.5 if sm_scale is None else float(sm_scale)
+    out = torch.empty((Lq, D), dtype=torch.bfloat16, device=q.device) if out is None else out
+    lse = torch.empty((H, Lq), dtype=torch.float32, device=q.device) if want_lse else None
+    rc = load().b200q_attn_bf16(_ptr(q), _ld(q), _ptr(k), _ld(k), _ptr(v), _ld(v), Lq, Lk, H, hd, sm_scale, _ptr(out), _ld(out),
+                                _ptr(lse), _stream())
+    _check(rc, "b200q_attn_bf16")
+    return (out, lse) if want_lse else out
 
 
 ATTN_MAX_KEYS = 65536        # int32 P.V accumulator bound of one kernel call: Lk * 255 * 127 < 2^31

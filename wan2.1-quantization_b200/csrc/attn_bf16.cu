@@ -1,0 +1,459 @@
+// bf16 flash attention on the 5th-gen tensor cores: the attention core of the W8A8 DiT step (BASELINE configs[1]/[3]).
+//
+// Replaces the reference's flash-attn call (ViDiT-Q/examples/Wan2.1/wan/modules/attention.py:94-127 =
+// flash_attn_varlen_func on bf16 q,k,v with softmax_scale = head_dim^-0.5, no mask, no dropout; the SDPA fallback
+// :171-178 is the same function): O = softmax(Q.K^T * scale) . V per head, head_dim = 128.
+//
+//   S   = Q.K^T          tcgen05.mma.kind::f16 (bf16 x bf16 -> fp32), A = Q tile and B = K tile from shared memory
+//                        (K-major, SWIZZLE_128B, written by TMA), D = 128x128 fp32 in TMEM
+//   P   = 2^(S*c - m)    softmax warpgroup, thread = query row = TMEM lane: tcgen05.ld S -> row max -> FFMA2 -> MUFU.EX2
+//                        -> bf16x2 -> tcgen05.st back into the S columns (P aliases S)
+//   O  += P.V            tcgen05.mma.kind::f16 with A = P read from TENSOR MEMORY and B = the V tile as it lies in global
+//                        memory ([keys, head_dim] = MN-major, SWIZZLE_128B): no transposed copy of V, no P round trip through
+//                        shared memory
+//   out = O / l          after the last key block
+//
+// Lazy rescaling: the running maximum m only moves (and O, l are only rescaled) when a block's row maximum exceeds it by
+// more than 2^8; until then P = 2^(x - m) simply exceeds 1 (bf16 has the exponent range, the fp32 accumulators the
+// headroom), so in steady state no thread touches O between the first and the last key block.  O is rescaled by the row's
+// own softmax thread (TMEM lane = row): legal exactly when P.V(j-1) has completed and P.V(j) has not been issued, which
+// the issue order below guarantees (S(j) complete implies P.V(j-1) complete: one in-order tensor pipe).
+//
+// CTA = 256 queries of one head (two 128-row Q tiles), persistent over (head, query-tile-pair) items; 10 warps:
+//   warps 0-3 / 4-7  softmax warpgroup of Q tile 0 / 1
+//   warp 8           TMA producer (Q tiles, K ring, V ring) + TMEM allocator
+//   warp 9           MMA issuer (one lane; warps 10, 11 idle: setmaxnreg works on whole warpgroups); issue order per key block j:  S0(j)  P1.V(j-1)  S1(j)  P0.V(j)
+// so the tensor pipe works on one tile while the other tile's warpgroup is in its softmax.
+// TMEM (512 columns): [S0/P0 | S1/P1 | O0 | O1], 128 columns each.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace b200q {
+using namespace ptx;
+
+int make_tmap_2d(CUtensorMap* out, const void* base, CUtensorMapDataType dt, int elem_bytes, int64_t rows, int64_t cols,
+                 int64_t ld, int box_rows, int box_cols, CUtensorMapSwizzle swz);
+
+namespace fa {
+
+constexpr int BQ = 128, BKEY = 128, HD = 128;
+constexpr int HALF = 128 * 64 * 2;          // one TMA box: 128 rows x 64 bf16 = 16 KB
+constexpr int TILE = 2 * HALF;              // a 128 x 128 bf16 operand tile = two boxes (head_dim halves)
+constexpr int KS = 2, VS = 2;
+constexpr int THREADS = 12 * 32;             // warpgroups 0, 1: softmax; warpgroup 2: TMA producer, MMA issuer, two idle warps
+constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+
+struct Smem {
+  static constexpr int q = 0;                       // 2 tiles
+  static constexpr int k = q + 2 * TILE;            // KS tiles
+  static constexpr int v = k + KS * TILE;           // VS tiles
+  static constexpr int bar = v + VS * TILE;
+  static constexpr int total = bar + 256;
+};
+static_assert(Smem::total <= 232448, "dynamic smem budget (227 KB) exceeded");
+
+struct Params {
+  int Lq, Lk, H;
+  __nv_bfloat16* out; long long ldo;
+  float scale_log2e;
+  int n_items, n_qt;
+  float* lse_out;                // optional [H, Lq]: log2(sum_j 2^(x_j)) per row, for key-split merges
+};
+
+// kind::f16 instruction descriptor: D = fp32, A = B = bf16, A K-major; B K-major (Q.K^T) or MN-major (P.V)
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// MN-major SWIZZLE_128B operand: 64-element (128 B) rows along MN, 8-row groups (1024 B) along K, MN atoms LBO apart
+// (cute/atom/mma_traits_sm100.hpp make_umma_desc<Major::MN>: ((8,n),(8,k)):((1,LBO),(8,SBO)) in 16-byte units)
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)(lbo_bytes >> 4) << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 -> fp32
+__device__ __forceinline__ void mma_bf16_ss(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem], bf16 -> fp32
+__device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]), "r"(v[19]), "r"(v[20]),
+      "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]),
+      "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]), "r"(v[10]),
+      "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ float ex2f(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+  return r;
+}
+
+// One 16-key chunk CH (0..7) of a 128-key block for one query row (thread = row): S chunk `sc` (already requested from
+// TMEM) -> P chunk (bf16x2 in pk; 16 TMEM columns are stored after every second chunk).  `sn` receives the prefetch of
+// chunk CH + 1.  16-column granularity keeps the register blocks of the TMEM loads / stores small.
+template <int CH>
+__device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)[16], uint32_t (&pk)[16], uint32_t t_s, uint32_t t_o,
+                                              int valid, bool have_o, float c, uint64_t c2, float& m_ref, uint64_t& sum2) {
+  tmem_ld_wait();
+  if (CH < 7) tmem_ld_32x16(t_s + (CH + 1) * 16, sn);
+  if (valid < BKEY) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (CH * 16 + e >= valid) sc[e] = 0xff800000u;   // -inf: P = 0
+  }
+  float mx0 = __uint_as_float(sc[0]), mx1 = __uint_as_float(sc[1]);
+#pragma unroll
+  for (int e = 2; e < 16; e += 2) {
+    mx0 = fmaxf(mx0, __uint_as_float(sc[e])); mx1 = fmaxf(mx1, __uint_as_float(sc[e + 1]));
+  }
+  const float bm = fmaxf(mx0, mx1) * c;                                  // c > 0
+  const bool need = bm > m_ref + RESCALE_THRESHOLD;                      // first chunk of an item: m_ref = -inf
+  if (__any_sync(0xffffffffu, need)) {
+    // ---- rare path: move the reference maximum; everything accumulated against the old one is rescaled ----
+    const float m_new = need ? bm : m_ref;
+    const float alpha = ex2f(m_ref - m_new);                             // 0 from -inf, exactly 1 for rows that keep m_ref
+    const uint64_t a2 = pack_f32x2(alpha, alpha);
+    sum2 = mul_f32x2(sum2, a2);
+    if (CH & 1) {                                                        // P of the previous chunk is still in registers
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        pk[i] = pack_bf16x2(__uint_as_float(pk[i] << 16) * alpha, __uint_as_float(pk[i] & 0xffff0000u) * alpha);
+    }
+    if (CH < 7) tmem_ld_wait();                                          // the prefetch must land before registers are reused
+#pragma unroll 1
+    for (int g = 0; g < (CH >> 1); ++g) {                                // P of the chunk pairs already stored to TMEM
+      uint32_t w[16];
+      tmem_ld_32x16(t_s + g * 16, w);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 16; ++i)
+        w[i] = pack_bf16x2(__uint_as_float(w[i] << 16) * alpha, __uint_as_float(w[i] & 0xffff0000u) * alpha);
+      tmem_st_32x16(t_s + g * 16, w);
+    }
+    if (have_o) {
+      // S(j) complete implies P.V(j-1) complete (in-order tensor pipe); P.V(j) waits for this warpgroup
+#pragma unroll 1
+      for (int oc = 0; oc < 8; ++oc) {
+        uint32_t o[16];
+        tmem_ld_32x16(t_o + oc * 16, o);
+        tmem_ld_wait();
+#pragma unroll
+        for (int e = 0; e < 16; e += 2) {
+          const uint64_t s2 = mul_f32x2(pack_u32x2(o[e], o[e + 1]), a2);
+          unpack_u32x2(s2, o[e], o[e + 1]);
+        }
+        tmem_st_32x16(t_o + oc * 16, o);
+      }
+    }
+    m_ref = m_new;
+  }
+  const float nm = -m_ref;
+  const uint64_t nm2 = pack_f32x2(nm, nm);
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    float x0, x1;
+    unpack_f32x2(fma_f32x2(pack_u32x2(sc[e], sc[e + 1]), c2, nm2), x0, x1);
+    const float p0 = ex2f(x0), p1 = ex2f(x1);
+    sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
+    pk[(CH & 1) * 8 + (e >> 1)] = pack_bf16x2(p0, p1);
+  }
+  if (CH & 1) tmem_st_32x16(t_s + (CH >> 1) * 16, pk);                   // P columns alias S chunks already consumed
+}
+
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                 const __grid_constant__ CUtensorMap tm_v, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("b200q: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+  uint64_t* q_full = bars;                 // 1
+  uint64_t* q_empty = q_full + 1;          // 1
+  uint64_t* k_full = q_empty + 1;          // KS
+  uint64_t* k_empty = k_full + KS;         // KS
+  uint64_t* v_full = k_empty + KS;         // VS
+  uint64_t* v_empty = v_full + VS;         // VS
+  uint64_t* s_full = v_empty + VS;         // [tile]: S(j) complete in TMEM
+  uint64_t* p_full = s_full + 2;           // [tile]: P(j) written to TMEM (and S(j) consumed)
+  uint64_t* o_full = p_full + 2;           // [tile]: O accumulator of the item complete
+  uint64_t* o_free = o_full + 2;           // [tile]: O read out by the warpgroup
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb = (p.Lk + BKEY - 1) / BKEY;
+
+  if (threadIdx.x == 0) {
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+    }
+    fence_barrier_init();
+  }
+  constexpr int W_TMA = 8, W_MMA = 9;
+  if (warp == W_TMA && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
+  if (warp == W_TMA) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  // register reconfiguration: the control warpgroup keeps 40 registers per thread, the softmax warpgroups (a whole S row of
+  // 128 fp32 values per thread) take 232
+  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+  else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+
+  if (warp == W_TMA) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
+        mbar_wait(q_empty, (it & 1) ^ 1);
+        mbar_expect_tx(q_full, 2 * TILE);
+#pragma unroll
+        for (int t = 0; t < 2; ++t)
+#pragma unroll
+          for (int hf = 0; hf < 2; ++hf)
+            tma_load_2d(smem + Smem::q + t * TILE + hf * HALF, &tm_q, q_full, h * HD + hf * 64, q0 + t * BQ);
+        for (int j = 0; j < nb; ++j) {
+          mbar_wait(&k_empty[ks], kph ^ 1);
+          mbar_expect_tx(&k_full[ks], TILE);
+          tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, j * BKEY);
+          tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, j * BKEY);
+          if (++ks == KS) { ks = 0; kph ^= 1; }
+          mbar_wait(&v_empty[vs], vph ^ 1);
+          mbar_expect_tx(&v_full[vs], TILE);
+          tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, j * BKEY);
+          tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, j * BKEY);
+          if (++vs == VS) { vs = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = idesc_bf16(BQ, BKEY, false);
+      constexpr uint32_t idesc_pv = idesc_bf16(BQ, HD, true);
+      int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
+      uint32_t pcnt[2] = {0, 0};                    // P tiles consumed so far per Q tile
+      const uint32_t q_addr = smem_u32(smem + Smem::q);
+      // S[t] = Q_t . K(stage)^T : 8 x (M128, N128, K16)
+      auto qk = [&](int t, int stage) {
+        const uint32_t ka = smem_u32(smem + Smem::k + stage * TILE);
+        const uint32_t d = tmem_base + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < HD / 16; ++kk) {
+          const uint64_t adesc = make_kmajor_sw128_desc(q_addr + t * TILE + (kk >> 2) * HALF) + (uint64_t)((kk & 3) * 2);
+          const uint64_t bdesc = make_kmajor_sw128_desc(ka + (kk >> 2) * HALF) + (uint64_t)((kk & 3) * 2);
+          mma_bf16_ss(d, adesc, bdesc, idesc_qk, kk != 0 ? 1u : 0u);
+        }
+        mma_commit(&s_full[t]);
+      };
+      // O[t] (+)= P_t (TMEM, bf16 packed in the S columns) . V(stage) : 8 x (M128, N128, K16)
+      auto pv = [&](int t, int stage, bool first) {
+        mbar_wait(&p_full[t], pcnt[t] & 1);
+        ++pcnt[t];
+        tcgen05_fence_after();
+        const uint32_t va = smem_u32(smem + Smem::v + stage * TILE);
+        const uint32_t d = tmem_base + 256 + t * 128;
+        const uint32_t pa = tmem_base + t * 128;
+#pragma unroll
+        for (int kk = 0; kk < BKEY / 16; ++kk) {
+          const uint64_t bdesc = make_mnmajor_sw128_desc(va + kk * 2048, HALF, 1024);
+          mma_bf16_ts(d, pa + kk * 8, bdesc, idesc_pv, (first && kk == 0) ? 0u : 1u);
+        }
+      };
+      auto next_k = [&]() { mma_commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
+      auto next_v = [&]() { mma_commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+        mbar_wait(q_full, it & 1);
+        mbar_wait(&k_full[ks], kph);
+        tcgen05_fence_after();
+        qk(0, ks);
+        qk(1, ks);
+        next_k();
+        mbar_wait(&o_free[0], it & 1);                         // previous item's O0 has been read out
+        mbar_wait(&v_full[vs], vph);
+        pv(0, vs, true);
+        for (int j = 1; j < nb; ++j) {
+          mbar_wait(&k_full[ks], kph);
+          tcgen05_fence_after();
+          qk(0, ks);                                           // S0(j): in order behind P0.V(j-1), which read P0 = S0's columns
+          if (j == 1) mbar_wait(&o_free[1], it & 1);
+          pv(1, vs, j == 1);                                   // P1.V(j-1)
+          next_v();
+          qk(1, ks);                                           // S1(j)
+          next_k();
+          mbar_wait(&v_full[vs], vph);
+          pv(0, vs, false);                                    // P0.V(j)
+        }
+        mma_commit(&o_full[0]);
+        mma_commit(q_empty);                                   // last read of the Q tiles was S1(nb-1)
+        if (nb == 1) mbar_wait(&o_free[1], it & 1);
+        pv(1, vs, nb == 1);                                    // P1.V(nb-1)
+        next_v();
+        mma_commit(&o_full[1]);
+      }
+    }
+  } else if (warp < 8) {
+    // ===================== softmax warpgroups =====================
+    const int t = warp >> 2, quarter = warp & 3;
+    const int r = quarter * 32 + lane;                                   // row inside the Q tile == TMEM lane
+    const uint32_t t_s = tmem_base + t * 128 + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t t_o = tmem_base + 256 + t * 128 + ((uint32_t)(quarter * 32) << 16);
+    uint32_t scnt = 0, itn = 0;
+    const float c = p.scale_log2e;
+    const uint64_t c2 = pack_f32x2(c, c);
+    const int tail = p.Lk - (nb - 1) * BKEY;                             // valid keys in the last block (1..128)
+    {                                                                    // O columns start out free
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[t]);
+    }
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
+      const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
+      const int row = q0 + r;
+      const bool row_ok = row < p.Lq;
+      float m_ref = -INFINITY;                                           // reference maximum of the exponentials (log2 units)
+      uint64_t sum2 = pack_f32x2(0.f, 0.f);
+      for (int j = 0; j < nb; ++j) {
+        mbar_wait(&s_full[t], scnt & 1);
+        ++scnt;
+        tcgen05_fence_after();
+        const int valid = (j == nb - 1) ? tail : BKEY;                   // keys of this block that exist
+        uint32_t sa[16], sb[16];                                         // S chunk ch lives in sa (even ch) / sb (odd ch)
+        uint32_t pk[16];                                                 // bf16x2 P of two chunks = 16 TMEM columns
+        tmem_ld_32x16(t_s, sa);
+        softmax_chunk<0>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<1>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<2>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<3>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<4>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<5>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<6>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        softmax_chunk<7>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+      }
+
+      // ---- read-out: out = O / l ----
+      float s0, s1;
+      unpack_f32x2(sum2, s0, s1);
+      const float l = s0 + s1;
+      const float inv = 1.0f / l;
+      mbar_wait(&o_full[t], itn & 1);
+      tcgen05_fence_after();
+      if (row_ok && p.lse_out != nullptr) p.lse_out[(long long)h * p.Lq + row] = m_ref + log2f(l);
+      __nv_bfloat16* g = p.out + (long long)(row_ok ? row : 0) * p.ldo + h * HD;
+#pragma unroll
+      for (int ch = 0; ch < 4; ++ch) {
+        uint32_t o[32];
+        tmem_ld_32x32(t_o + ch * 32, o);
+        tmem_ld_wait();
+        if (ch == 3) {                                                   // O is in registers: hand the columns back
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_free[t]);
+        }
+        if (row_ok) {
+#pragma unroll
+          for (int e = 0; e < 32; e += 8) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv);
+            w.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
+            w.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
+            w.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
+            *reinterpret_cast<uint4*>(g + ch * 32 + e) = w;
+          }
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  if (warp == W_TMA) tmem_dealloc<512>(tmem_base);
+}
+
+}  // namespace fa
+}  // namespace b200q
+
+using namespace b200q;
+
+extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                               int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
+                               float* lse_out, b200q_stream_t stream) {
+  clear_error();
+  using namespace fa;
+  B200Q_REQUIRE(q && k && v && out, B200Q_ERR_BAD_ARG, "attn_bf16: null pointer");
+  B200Q_REQUIRE(Lq > 0 && Lk > 0 && num_heads > 0, B200Q_ERR_BAD_ARG, "attn_bf16: bad shape");
+  B200Q_REQUIRE(head_dim == HD, B200Q_ERR_UNSUPPORTED, "attn_bf16: head_dim must be 128 (Wan2.1: 1536/12 = 5120/40 = 128)");
+  B200Q_REQUIRE(Lq < (1ll << 31) - 512 && Lk < (1ll << 31) - 512, B200Q_ERR_UNSUPPORTED, "attn_bf16: sequence too long");
+  const int64_t D = (int64_t)num_heads * HD;
+  B200Q_REQUIRE(ldq >= D && ldk >= D && ldv >= D && ldo >= D, B200Q_ERR_BAD_ARG, "attn_bf16: leading dimension < heads*128");
+  B200Q_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned(q, 16) && aligned(k, 16) && aligned(v, 16) &&
+                    aligned(out, 16),
+                B200Q_ERR_BAD_ARG, "attn_bf16: q/k/v/out must be 16-byte aligned bf16 with row pitches that are multiples of 8");
+  CUtensorMap tq, tk, tv;
+  int rc;
+  if ((rc = make_tmap_2d(&tq, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lq, D, ldq, BQ, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_2d(&tk, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldk, BKEY, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_2d(&tv, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldv, BKEY, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  Params p{};
+  p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = num_heads;
+  p.out = (__nv_bfloat16*)out; p.ldo = ldo;
+  p.scale_log2e = sm_scale * 1.4426950408889634f;
+  p.n_qt = (int)((Lq + 2 * BQ - 1) / (2 * BQ));
+  p.n_items = p.n_qt * num_heads;
+  p.lse_out = lse_out;
+  static bool configured = false;
+  if (!configured) {
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    configured = true;
+  }
+  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
+  attn_bf16_kernel<<<grid, THREADS, Smem::total, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
