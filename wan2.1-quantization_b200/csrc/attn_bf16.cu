@@ -39,7 +39,7 @@ namespace fa {
 constexpr int BQ = 128, BKEY = 128, HD = 128;
 constexpr int HALF = 128 * 64 * 2;          // one TMA box: 128 rows x 64 bf16 = 16 KB
 constexpr int TILE = 2 * HALF;              // a 128 x 128 bf16 operand tile = two boxes (head_dim halves)
-constexpr int KS = 2, VS = 2;
+constexpr int KS = 3, VS = 2;
 constexpr int THREADS = 12 * 32;             // warpgroups 0, 1: softmax; warpgroup 2: TMA producer, MMA issuer, two idle warps
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
@@ -122,17 +122,65 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// One 16-key chunk CH (0..7) of a 128-key block for one query row (thread = row): S chunk `sc` (already requested from
-// TMEM) -> P chunk (bf16x2 in pk; 16 TMEM columns are stored after every second chunk).  `sn` receives the prefetch of
-// chunk CH + 1.  16-column granularity keeps the register blocks of the TMEM loads / stores small.
-template <int CH>
-__device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)[16], uint32_t (&pk)[16], uint32_t t_s, uint32_t t_o,
-                                              int valid, bool have_o, float c, uint64_t c2, float& m_ref, uint64_t& sum2) {
-  tmem_ld_wait();
-  if (CH < 7) tmem_ld_32x16(t_s + (CH + 1) * 16, sn);
-  if (valid < BKEY) {
+// Bounded mbarrier wait without the diagnostic printf of ptx::mbar_wait (code size: the softmax loop has to stay inside
+// the instruction cache); a protocol bug still surfaces as a launch failure.
+__device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint32_t spins = 0;
+  long long t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 255u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) __trap();
+    }
+  }
+}
+
+// Rare path of the lazy rescaling: multiply the P groups of this block already stored to TMEM and, if present, the O
+// accumulator row by alpha (rolled loops: this code exists twice per kernel and runs a handful of times per row).
+__device__ __forceinline__ void rescale_tmem(uint32_t t_s, uint32_t t_o, float alpha, int p_groups, bool have_o) {
+  const uint64_t a2 = pack_f32x2(alpha, alpha);
+#pragma unroll 1
+  for (int g = 0; g < p_groups; ++g) {
+    uint32_t w[16];
+    tmem_ld_32x16(t_s + g * 16, w);
+    tmem_ld_wait();
 #pragma unroll
-    for (int e = 0; e < 16; ++e) if (CH * 16 + e >= valid) sc[e] = 0xff800000u;   // -inf: P = 0
+    for (int i = 0; i < 16; ++i)
+      w[i] = pack_bf16x2(__uint_as_float(w[i] << 16) * alpha, __uint_as_float(w[i] & 0xffff0000u) * alpha);
+    tmem_st_32x16(t_s + g * 16, w);
+  }
+  if (have_o) {
+    // S(j) complete implies P.V(j-1) complete (in-order tensor pipe); P.V(j) waits for this warpgroup
+#pragma unroll 1
+    for (int oc = 0; oc < 8; ++oc) {
+      uint32_t o[16];
+      tmem_ld_32x16(t_o + oc * 16, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int e = 0; e < 16; e += 2) {
+        const uint64_t s2 = mul_f32x2(pack_u32x2(o[e], o[e + 1]), a2);
+        unpack_u32x2(s2, o[e], o[e + 1]);
+      }
+      tmem_st_32x16(t_o + oc * 16, o);
+    }
+  }
+}
+
+// One 16-key chunk (index 2*g + PAR of the 128-key block) for one query row (thread = row): S chunk `sc` (already
+// requested from TMEM) -> P chunk (bf16x2 into pk[PAR*8 ..]).  `sn` receives the prefetch of the next chunk (`more`).
+// 16-column granularity keeps the register blocks of the TMEM loads / stores small.
+template <int PAR>
+__device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)[16], uint32_t (&pk)[16], uint32_t t_s, uint32_t t_o,
+                                              int g, bool more, int valid, bool have_o, float c, uint64_t c2, float& m_ref,
+                                              uint64_t& sum2) {
+  tmem_ld_wait();
+  if (more) tmem_ld_32x16(t_s + (2 * g + PAR + 1) * 16, sn);
+  if (valid < BKEY) {
+    const int base = (2 * g + PAR) * 16;
+#pragma unroll
+    for (int e = 0; e < 16; ++e) if (base + e >= valid) sc[e] = 0xff800000u;   // -inf: P = 0
   }
   float mx0 = __uint_as_float(sc[0]), mx1 = __uint_as_float(sc[1]);
 #pragma unroll
@@ -145,39 +193,14 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)
     // ---- rare path: move the reference maximum; everything accumulated against the old one is rescaled ----
     const float m_new = need ? bm : m_ref;
     const float alpha = ex2f(m_ref - m_new);                             // 0 from -inf, exactly 1 for rows that keep m_ref
-    const uint64_t a2 = pack_f32x2(alpha, alpha);
-    sum2 = mul_f32x2(sum2, a2);
-    if (CH & 1) {                                                        // P of the previous chunk is still in registers
+    sum2 = mul_f32x2(sum2, pack_f32x2(alpha, alpha));
+    if (PAR == 1) {                                                      // P of the previous chunk is still in registers
 #pragma unroll
       for (int i = 0; i < 8; ++i)
         pk[i] = pack_bf16x2(__uint_as_float(pk[i] << 16) * alpha, __uint_as_float(pk[i] & 0xffff0000u) * alpha);
     }
-    if (CH < 7) tmem_ld_wait();                                          // the prefetch must land before registers are reused
-#pragma unroll 1
-    for (int g = 0; g < (CH >> 1); ++g) {                                // P of the chunk pairs already stored to TMEM
-      uint32_t w[16];
-      tmem_ld_32x16(t_s + g * 16, w);
-      tmem_ld_wait();
-#pragma unroll
-      for (int i = 0; i < 16; ++i)
-        w[i] = pack_bf16x2(__uint_as_float(w[i] << 16) * alpha, __uint_as_float(w[i] & 0xffff0000u) * alpha);
-      tmem_st_32x16(t_s + g * 16, w);
-    }
-    if (have_o) {
-      // S(j) complete implies P.V(j-1) complete (in-order tensor pipe); P.V(j) waits for this warpgroup
-#pragma unroll 1
-      for (int oc = 0; oc < 8; ++oc) {
-        uint32_t o[16];
-        tmem_ld_32x16(t_o + oc * 16, o);
-        tmem_ld_wait();
-#pragma unroll
-        for (int e = 0; e < 16; e += 2) {
-          const uint64_t s2 = mul_f32x2(pack_u32x2(o[e], o[e + 1]), a2);
-          unpack_u32x2(s2, o[e], o[e + 1]);
-        }
-        tmem_st_32x16(t_o + oc * 16, o);
-      }
-    }
+    if (more) tmem_ld_wait();                                            // the prefetch must land before its registers are reused
+    rescale_tmem(t_s, t_o, alpha, g, have_o);
     m_ref = m_new;
   }
   const float nm = -m_ref;
@@ -188,9 +211,8 @@ __device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)
     unpack_f32x2(fma_f32x2(pack_u32x2(sc[e], sc[e + 1]), c2, nm2), x0, x1);
     const float p0 = ex2f(x0), p1 = ex2f(x1);
     sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
-    pk[(CH & 1) * 8 + (e >> 1)] = pack_bf16x2(p0, p1);
+    pk[PAR * 8 + (e >> 1)] = pack_bf16x2(p0, p1);
   }
-  if (CH & 1) tmem_st_32x16(t_s + (CH >> 1) * 16, pk);                   // P columns alias S chunks already consumed
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -246,7 +268,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
         const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
-        mbar_wait(q_empty, (it & 1) ^ 1);
+        bar_wait(q_empty, (it & 1) ^ 1);
         mbar_expect_tx(q_full, 2 * TILE);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -254,12 +276,12 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           for (int hf = 0; hf < 2; ++hf)
             tma_load_2d(smem + Smem::q + t * TILE + hf * HALF, &tm_q, q_full, h * HD + hf * 64, q0 + t * BQ);
         for (int j = 0; j < nb; ++j) {
-          mbar_wait(&k_empty[ks], kph ^ 1);
+          bar_wait(&k_empty[ks], kph ^ 1);
           mbar_expect_tx(&k_full[ks], TILE);
           tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, j * BKEY);
           tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, j * BKEY);
           if (++ks == KS) { ks = 0; kph ^= 1; }
-          mbar_wait(&v_empty[vs], vph ^ 1);
+          bar_wait(&v_empty[vs], vph ^ 1);
           mbar_expect_tx(&v_full[vs], TILE);
           tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, j * BKEY);
           tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, j * BKEY);
@@ -269,69 +291,79 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
   } else if (warp == W_MMA) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk = idesc_bf16(BQ, BKEY, false);
-      constexpr uint32_t idesc_pv = idesc_bf16(BQ, HD, true);
-      int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
-      uint32_t pcnt[2] = {0, 0};                    // P tiles consumed so far per Q tile
-      const uint32_t q_addr = smem_u32(smem + Smem::q);
-      // S[t] = Q_t . K(stage)^T : 8 x (M128, N128, K16)
-      auto qk = [&](int t, int stage) {
-        const uint32_t ka = smem_u32(smem + Smem::k + stage * TILE);
-        const uint32_t d = tmem_base + t * 128;
+    // The whole warp walks the schedule (uniform control flow keeps descriptors and addresses in uniform registers); one
+    // elected lane issues the tcgen05 instructions.
+    constexpr uint32_t idesc_qk = idesc_bf16(BQ, BKEY, false);
+    constexpr uint32_t idesc_pv = idesc_bf16(BQ, HD, true);
+    int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
+    uint32_t pcnt0 = 0, pcnt1 = 0;                    // P tiles consumed so far per Q tile
+    const uint64_t qd0 = make_kmajor_sw128_desc(smem_u32(smem + Smem::q));
+    const uint64_t qd1 = make_kmajor_sw128_desc(smem_u32(smem + Smem::q + TILE));
+    const uint64_t kd = make_kmajor_sw128_desc(smem_u32(smem + Smem::k));
+    const uint64_t vd = make_mnmajor_sw128_desc(smem_u32(smem + Smem::v), HALF, 1024);
+    // S[t] = Q_t . K(stage)^T : 8 x (M128, N128, K16); k-step kk: head_dim half kk / 4, 32 bytes per step inside the 128 B row
+    auto qk = [&](int t, int stage) {
+      const uint64_t a0 = t ? qd1 : qd0;
+      const uint64_t b0 = kd + (uint64_t)(stage * (TILE >> 4));
+      const uint32_t d = tmem_base + t * 128;
+      if (elect_one()) {
 #pragma unroll
         for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint64_t adesc = make_kmajor_sw128_desc(q_addr + t * TILE + (kk >> 2) * HALF) + (uint64_t)((kk & 3) * 2);
-          const uint64_t bdesc = make_kmajor_sw128_desc(ka + (kk >> 2) * HALF) + (uint64_t)((kk & 3) * 2);
-          mma_bf16_ss(d, adesc, bdesc, idesc_qk, kk != 0 ? 1u : 0u);
+          const uint64_t off = (uint64_t)((kk >> 2) * (HALF >> 4) + (kk & 3) * 2);
+          mma_bf16_ss(d, a0 + off, b0 + off, idesc_qk, kk != 0 ? 1u : 0u);
         }
         mma_commit(&s_full[t]);
-      };
-      // O[t] (+)= P_t (TMEM, bf16 packed in the S columns) . V(stage) : 8 x (M128, N128, K16)
-      auto pv = [&](int t, int stage, bool first) {
-        mbar_wait(&p_full[t], pcnt[t] & 1);
-        ++pcnt[t];
-        tcgen05_fence_after();
-        const uint32_t va = smem_u32(smem + Smem::v + stage * TILE);
-        const uint32_t d = tmem_base + 256 + t * 128;
-        const uint32_t pa = tmem_base + t * 128;
-#pragma unroll
-        for (int kk = 0; kk < BKEY / 16; ++kk) {
-          const uint64_t bdesc = make_mnmajor_sw128_desc(va + kk * 2048, HALF, 1024);
-          mma_bf16_ts(d, pa + kk * 8, bdesc, idesc_pv, (first && kk == 0) ? 0u : 1u);
-        }
-      };
-      auto next_k = [&]() { mma_commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
-      auto next_v = [&]() { mma_commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        mbar_wait(q_full, it & 1);
-        mbar_wait(&k_full[ks], kph);
-        tcgen05_fence_after();
-        qk(0, ks);
-        qk(1, ks);
-        next_k();
-        mbar_wait(&o_free[0], it & 1);                         // previous item's O0 has been read out
-        mbar_wait(&v_full[vs], vph);
-        pv(0, vs, true);
-        for (int j = 1; j < nb; ++j) {
-          mbar_wait(&k_full[ks], kph);
-          tcgen05_fence_after();
-          qk(0, ks);                                           // S0(j): in order behind P0.V(j-1), which read P0 = S0's columns
-          if (j == 1) mbar_wait(&o_free[1], it & 1);
-          pv(1, vs, j == 1);                                   // P1.V(j-1)
-          next_v();
-          qk(1, ks);                                           // S1(j)
-          next_k();
-          mbar_wait(&v_full[vs], vph);
-          pv(0, vs, false);                                    // P0.V(j)
-        }
-        mma_commit(&o_full[0]);
-        mma_commit(q_empty);                                   // last read of the Q tiles was S1(nb-1)
-        if (nb == 1) mbar_wait(&o_free[1], it & 1);
-        pv(1, vs, nb == 1);                                    // P1.V(nb-1)
-        next_v();
-        mma_commit(&o_full[1]);
       }
+      __syncwarp();
+    };
+    // O[t] (+)= P_t (TMEM, bf16 packed in the S columns) . V(stage) : 8 x (M128, N128, K16); 16 keys = 2048 B of the V tile
+    auto pv = [&](int t, int stage, bool first) {
+      if (t == 0) { bar_wait(&p_full[0], pcnt0 & 1); ++pcnt0; } else { bar_wait(&p_full[1], pcnt1 & 1); ++pcnt1; }
+      tcgen05_fence_after();
+      const uint64_t b0 = vd + (uint64_t)(stage * (TILE >> 4));
+      const uint32_t d = tmem_base + 256 + t * 128;
+      const uint32_t pa = tmem_base + t * 128;
+      if (elect_one()) {
+#pragma unroll
+        for (int kk = 0; kk < BKEY / 16; ++kk)
+          mma_bf16_ts(d, pa + kk * 8, b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (first && kk == 0) ? 0u : 1u);
+      }
+      __syncwarp();
+    };
+    auto commit = [&](uint64_t* bar) {
+      if (elect_one()) mma_commit(bar);
+      __syncwarp();
+    };
+    auto next_k = [&]() { commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
+    auto next_v = [&]() { commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      bar_wait(q_full, it & 1);
+      bar_wait(&k_full[ks], kph);
+      tcgen05_fence_after();
+      qk(0, ks);
+      qk(1, ks);
+      next_k();
+      bar_wait(&o_free[0], it & 1);                         // previous item's O0 has been read out
+      bar_wait(&v_full[vs], vph);
+      pv(0, vs, true);
+      for (int j = 1; j < nb; ++j) {
+        bar_wait(&k_full[ks], kph);
+        tcgen05_fence_after();
+        qk(0, ks);                                           // S0(j): in order behind P0.V(j-1), which read P0 = S0's columns
+        if (j == 1) bar_wait(&o_free[1], it & 1);
+        pv(1, vs, j == 1);                                   // P1.V(j-1)
+        next_v();
+        qk(1, ks);                                           // S1(j)
+        next_k();
+        bar_wait(&v_full[vs], vph);
+        pv(0, vs, false);                                    // P0.V(j)
+      }
+      commit(&o_full[0]);
+      commit(q_empty);                                       // last read of the Q tiles was S1(nb-1)
+      if (nb == 1) bar_wait(&o_free[1], it & 1);
+      pv(1, vs, nb == 1);                                    // P1.V(nb-1)
+      next_v();
+      commit(&o_full[1]);
     }
   } else if (warp < 8) {
     // ===================== softmax warpgroups =====================
@@ -355,21 +387,19 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       float m_ref = -INFINITY;                                           // reference maximum of the exponentials (log2 units)
       uint64_t sum2 = pack_f32x2(0.f, 0.f);
       for (int j = 0; j < nb; ++j) {
-        mbar_wait(&s_full[t], scnt & 1);
+        bar_wait(&s_full[t], scnt & 1);
         ++scnt;
         tcgen05_fence_after();
         const int valid = (j == nb - 1) ? tail : BKEY;                   // keys of this block that exist
-        uint32_t sa[16], sb[16];                                         // S chunk ch lives in sa (even ch) / sb (odd ch)
-        uint32_t pk[16];                                                 // bf16x2 P of two chunks = 16 TMEM columns
+        uint32_t sa[16], sb[16];                                         // S chunks 2g / 2g+1 live in sa / sb
+        uint32_t pk[16];                                                 // bf16x2 P of one chunk pair = 16 TMEM columns
         tmem_ld_32x16(t_s, sa);
-        softmax_chunk<0>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<1>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<2>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<3>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<4>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<5>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<6>(sa, sb, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
-        softmax_chunk<7>(sb, sa, pk, t_s, t_o, valid, j > 0, c, c2, m_ref, sum2);
+#pragma unroll 1
+        for (int g = 0; g < 4; ++g) {
+          softmax_chunk<0>(sa, sb, pk, t_s, t_o, g, true, valid, j > 0, c, c2, m_ref, sum2);
+          softmax_chunk<1>(sb, sa, pk, t_s, t_o, g, g < 3, valid, j > 0, c, c2, m_ref, sum2);
+          tmem_st_32x16(t_s + g * 16, pk);                               // P columns alias S chunks already consumed
+        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -381,7 +411,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       unpack_f32x2(sum2, s0, s1);
       const float l = s0 + s1;
       const float inv = 1.0f / l;
-      mbar_wait(&o_full[t], itn & 1);
+      bar_wait(&o_full[t], itn & 1);
       tcgen05_fence_after();
       if (row_ok && p.lse_out != nullptr) p.lse_out[(long long)h * p.Lq + row] = m_ref + log2f(l);
       __nv_bfloat16* g = p.out + (long long)(row_ok ? row : 0) * p.ldo + h * HD;
