@@ -241,6 +241,10 @@ B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t
                     int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
                     float* lse_out, b200q_stream_t stream);
 
+/* Scheduling knob of b200q_attn_bf16 (debug / benchmarking; results identical): bit 0 = the softmax warpgroups of the two
+ * query tiles take turns in their exponential sections instead of running concurrently. */
+B200Q_API int b200q_attn_bf16_set_mode(int mode);
+
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the
  *   [L*H, 128] view); dq/dk: their fp32 scales, element (token, head) at dq[token*dq_tok_stride + head*dq_head_stride];

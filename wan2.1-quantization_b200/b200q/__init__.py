@@ -63,6 +63,7 @@ _SIGNATURES = {
                               c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_int,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_attn_set_mode": (c_int, [c_int]),
+    "b200q_attn_bf16_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
                                 c_void_p, c_int64, c_void_p, c_void_p]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
@@ -406,6 +407,11 @@ def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False):
                                 _ptr(lse), _stream())
     _check(rc, "b200q_attn_bf16")
     return (out, lse) if want_lse else out
+
+
+def attn_bf16_set_mode(mode):
+    if load().b200q_attn_bf16_set_mode(int(mode)) != 0:
+        raise B200QError("b200q_attn_bf16_set_mode: bad mode")
 
 
 ATTN_MAX_KEYS = 65536        # int32 P.V accumulator bound of one kernel call: Lk * 255 * 127 < 2^31

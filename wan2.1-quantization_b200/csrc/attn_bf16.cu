@@ -19,11 +19,14 @@
 // own softmax thread (TMEM lane = row): legal exactly when P.V(j-1) has completed and P.V(j) has not been issued, which
 // the issue order below guarantees (S(j) complete implies P.V(j-1) complete: one in-order tensor pipe).
 //
-// CTA = 256 queries of one head (two 128-row Q tiles), persistent over (head, query-tile-pair) items; 10 warps:
-//   warps 0-3 / 4-7  softmax warpgroup of Q tile 0 / 1
-//   warp 8           TMA producer (Q tiles, K ring, V ring) + TMEM allocator
-//   warp 9           MMA issuer (one lane; warps 10, 11 idle: setmaxnreg works on whole warpgroups); issue order per key block j:  S0(j)  P1.V(j-1)  S1(j)  P0.V(j)
-// so the tensor pipe works on one tile while the other tile's warpgroup is in its softmax.
+// CTA = 256 queries of one head (two 128-row Q tiles), persistent over (head, query-tile-pair) items; 18 warps:
+//   warps 0-7 / 8-15  softmax warps of Q tile 0 / 1: TWO threads per query row (TMEM lane), 64 key columns each - the
+//                     per-tile chain S -> softmax -> P.V -> next S is the critical path, so the softmax of a tile is spread
+//                     over 8 warps; the two half-row maxima / sums meet through shared memory and a named barrier
+//   warp 16           TMA producer (Q tiles, K ring, V ring) + TMEM allocator
+//   warp 17           MMA issuer (whole warp walks the schedule, one elected lane issues);
+//                     issue order per key block j:  S0(j)  P1.V(j-1)  S1(j)  P0.V(j)
+// so the tensor pipe works on one tile while the other tile's warps are in their softmax.
 // TMEM (512 columns): [S0/P0 | S1/P1 | O0 | O1], 128 columns each.
 #include "common.cuh"
 #include "ptx.cuh"
@@ -39,15 +42,17 @@ namespace fa {
 constexpr int BQ = 128, BKEY = 128, HD = 128;
 constexpr int HALF = 128 * 64 * 2;          // one TMA box: 128 rows x 64 bf16 = 16 KB
 constexpr int TILE = 2 * HALF;              // a 128 x 128 bf16 operand tile = two boxes (head_dim halves)
-constexpr int KS = 3, VS = 2;
-constexpr int THREADS = 12 * 32;             // warpgroups 0, 1: softmax; warpgroup 2: TMA producer, MMA issuer, two idle warps
+constexpr int KS = 2, VS = 2;
+constexpr int THREADS = 18 * 32;             // 16 softmax warps + TMA producer + MMA issuer
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
+constexpr int POLY_PAIRS = 2;               // of every 8 element pairs, this many take the polynomial exp2 (25 %)
 
 struct Smem {
   static constexpr int q = 0;                       // 2 tiles
   static constexpr int k = q + 2 * TILE;            // KS tiles
   static constexpr int v = k + KS * TILE;           // VS tiles
-  static constexpr int bar = v + VS * TILE;
+  static constexpr int xch = v + VS * TILE;          // half-row statistics exchange: [tile][parity][half][row] fp32
+  static constexpr int bar = xch + 2 * 2 * 2 * 128 * 4;
   static constexpr int total = bar + 256;
 };
 static_assert(Smem::total <= 232448, "dynamic smem budget (227 KB) exceeded");
@@ -57,6 +62,7 @@ struct Params {
   __nv_bfloat16* out; long long ldo;
   float scale_log2e;
   int n_items, n_qt;
+  int mode;                      // scheduling knob (b200q_attn_bf16_set_mode)
   float* lse_out;                // optional [H, Lq]: log2(sum_j 2^(x_j)) per row, for key-split merges
 };
 
@@ -137,82 +143,75 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
-// Rare path of the lazy rescaling: multiply the P groups of this block already stored to TMEM and, if present, the O
-// accumulator row by alpha (rolled loops: this code exists twice per kernel and runs a handful of times per row).
-__device__ __forceinline__ void rescale_tmem(uint32_t t_s, uint32_t t_o, float alpha, int p_groups, bool have_o) {
+// Rare path of the lazy rescaling: multiply this thread's 64 columns of the O accumulator row by alpha (rolled loop: runs
+// a handful of times per row).
+__device__ __forceinline__ void rescale_o(uint32_t t_o, float alpha) {
   const uint64_t a2 = pack_f32x2(alpha, alpha);
 #pragma unroll 1
-  for (int g = 0; g < p_groups; ++g) {
-    uint32_t w[16];
-    tmem_ld_32x16(t_s + g * 16, w);
+  for (int oc = 0; oc < 4; ++oc) {
+    uint32_t o[16];
+    tmem_ld_32x16(t_o + oc * 16, o);
     tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < 16; ++i)
-      w[i] = pack_bf16x2(__uint_as_float(w[i] << 16) * alpha, __uint_as_float(w[i] & 0xffff0000u) * alpha);
-    tmem_st_32x16(t_s + g * 16, w);
-  }
-  if (have_o) {
-    // S(j) complete implies P.V(j-1) complete (in-order tensor pipe); P.V(j) waits for this warpgroup
-#pragma unroll 1
-    for (int oc = 0; oc < 8; ++oc) {
-      uint32_t o[16];
-      tmem_ld_32x16(t_o + oc * 16, o);
-      tmem_ld_wait();
-#pragma unroll
-      for (int e = 0; e < 16; e += 2) {
-        const uint64_t s2 = mul_f32x2(pack_u32x2(o[e], o[e + 1]), a2);
-        unpack_u32x2(s2, o[e], o[e + 1]);
-      }
-      tmem_st_32x16(t_o + oc * 16, o);
+    for (int e = 0; e < 16; e += 2) {
+      const uint64_t s2 = mul_f32x2(pack_u32x2(o[e], o[e + 1]), a2);
+      unpack_u32x2(s2, o[e], o[e + 1]);
     }
+    tmem_st_32x16(t_o + oc * 16, o);
   }
 }
 
-// One 16-key chunk (index 2*g + PAR of the 128-key block) for one query row (thread = row): S chunk `sc` (already
-// requested from TMEM) -> P chunk (bf16x2 into pk[PAR*8 ..]).  `sn` receives the prefetch of the next chunk (`more`).
-// 16-column granularity keeps the register blocks of the TMEM loads / stores small.
-template <int PAR>
-__device__ __forceinline__ void softmax_chunk(uint32_t (&sc)[16], uint32_t (&sn)[16], uint32_t (&pk)[16], uint32_t t_s, uint32_t t_o,
-                                              int g, bool more, int valid, bool have_o, float c, uint64_t c2, float& m_ref,
-                                              uint64_t& sum2) {
-  tmem_ld_wait();
-  if (more) tmem_ld_32x16(t_s + (2 * g + PAR + 1) * 16, sn);
-  if (valid < BKEY) {
-    const int base = (2 * g + PAR) * 16;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) if (base + e >= valid) sc[e] = 0xff800000u;   // -inf: P = 0
-  }
-  float mx0 = __uint_as_float(sc[0]), mx1 = __uint_as_float(sc[1]);
-#pragma unroll
-  for (int e = 2; e < 16; e += 2) {
-    mx0 = fmaxf(mx0, __uint_as_float(sc[e])); mx1 = fmaxf(mx1, __uint_as_float(sc[e + 1]));
-  }
-  const float bm = fmaxf(mx0, mx1) * c;                                  // c > 0
-  const bool need = bm > m_ref + RESCALE_THRESHOLD;                      // first chunk of an item: m_ref = -inf
-  if (__any_sync(0xffffffffu, need)) {
-    // ---- rare path: move the reference maximum; everything accumulated against the old one is rescaled ----
-    const float m_new = need ? bm : m_ref;
-    const float alpha = ex2f(m_ref - m_new);                             // 0 from -inf, exactly 1 for rows that keep m_ref
-    sum2 = mul_f32x2(sum2, pack_f32x2(alpha, alpha));
-    if (PAR == 1) {                                                      // P of the previous chunk is still in registers
-#pragma unroll
-      for (int i = 0; i < 8; ++i)
-        pk[i] = pack_bf16x2(__uint_as_float(pk[i] << 16) * alpha, __uint_as_float(pk[i] & 0xffff0000u) * alpha);
-    }
-    if (more) tmem_ld_wait();                                            // the prefetch must land before its registers are reused
-    rescale_tmem(t_s, t_o, alpha, g, have_o);
-    m_ref = m_new;
-  }
-  const float nm = -m_ref;
-  const uint64_t nm2 = pack_f32x2(nm, nm);
+// 2^x for two lanes on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + r, r in [-0.5, 0.5], degree-4 minimax
+// polynomial for 2^r (max relative error 7e-6, far below the bf16 rounding of P), 2^n by integer addition into the
+// exponent field.  The softmax is bound by the 16 MUFU.EX2 per clock per SM; routing a quarter of the exponentials through
+// this path takes the MUFU off the critical path (the technique FlashAttention-4 uses on the same hardware).
+__device__ __forceinline__ uint64_t exp2_poly2(uint64_t x2) {
+  const uint64_t magic2 = pack_f32x2(12582912.0f, 12582912.0f), nmagic2 = pack_f32x2(-12582912.0f, -12582912.0f);
+  float x0, x1;
+  unpack_f32x2(x2, x0, x1);
+  const uint64_t xc = pack_f32x2(fmaxf(x0, -126.f), fmaxf(x1, -126.f));
+  const uint64_t t = add_f32x2(xc, magic2);                              // integer part n = rne(x) in the low mantissa bits
+  const uint64_t r = add_f32x2(xc, mul_f32x2(add_f32x2(t, nmagic2), pack_f32x2(-1.f, -1.f)));   // r = x - n
+  uint64_t q = fma_f32x2(r, pack_f32x2(0.009670767933130264f, 0.009670767933130264f), pack_f32x2(0.05587553605437279f, 0.05587553605437279f));
+  q = fma_f32x2(q, r, pack_f32x2(0.24022211134433746f, 0.24022211134433746f));
+  q = fma_f32x2(q, r, pack_f32x2(0.6931272745132446f, 0.6931272745132446f));
+  q = fma_f32x2(q, r, pack_f32x2(1.0f, 1.0f));
+  uint32_t q0, q1, t0, t1;
+  unpack_u32x2(q, q0, q1);
+  unpack_u32x2(t, t0, t1);
+  return pack_u32x2(q0 + (t0 << 23), q1 + (t1 << 23));                   // (magic + n) << 23 == n << 23 (mod 2^32)
+}
+
+// P = 2^(S*c - m) for one 16-key chunk: bf16x2 codes into pk[0..7], fp32 row sum into sum2.  POLY pairs of the 8 go through
+// the polynomial, the rest through MUFU.EX2.
+template <int POLY>
+__device__ __forceinline__ void exp_chunk(const uint32_t (&sc)[16], uint32_t* pk, uint64_t c2, uint64_t nm2, uint64_t& sum2) {
 #pragma unroll
   for (int e = 0; e < 16; e += 2) {
-    float x0, x1;
-    unpack_f32x2(fma_f32x2(pack_u32x2(sc[e], sc[e + 1]), c2, nm2), x0, x1);
-    const float p0 = ex2f(x0), p1 = ex2f(x1);
-    sum2 = add_f32x2(sum2, pack_f32x2(p0, p1));
-    pk[PAR * 8 + (e >> 1)] = pack_bf16x2(p0, p1);
+    const uint64_t x2 = fma_f32x2(pack_u32x2(sc[e], sc[e + 1]), c2, nm2);
+    uint64_t p2;
+    if ((e >> 1) < POLY) {
+      p2 = exp2_poly2(x2);
+    } else {
+      float x0, x1;
+      unpack_f32x2(x2, x0, x1);
+      p2 = pack_f32x2(ex2f(x0), ex2f(x1));
+    }
+    sum2 = add_f32x2(sum2, p2);
+    float p0, p1;
+    unpack_f32x2(p2, p0, p1);
+    pk[e >> 1] = pack_bf16x2(p0, p1);
   }
+}
+
+__device__ __forceinline__ float max16(const uint32_t (&sc)[16], float m) {
+  float m0 = m, m1 = m;
+#pragma unroll
+  for (int e = 0; e < 16; e += 4) {
+    m0 = fmaxf(m0, fmaxf(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])));
+    m1 = fmaxf(m1, fmaxf(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])));
+  }
+  return fmaxf(m0, m1);
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -244,23 +243,18 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
     for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4);
-      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 4);
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8);
     }
     fence_barrier_init();
   }
-  constexpr int W_TMA = 8, W_MMA = 9;
+  constexpr int W_TMA = 16, W_MMA = 17;
   if (warp == W_TMA && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
   if (warp == W_TMA) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-
-  // register reconfiguration: the control warpgroup keeps 40 registers per thread, the softmax warpgroups (a whole S row of
-  // 128 fp32 values per thread) take 232
-  if (warp >= 8) asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-  else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
 
   if (warp == W_TMA) {
     // ===================== TMA producer =====================
@@ -365,13 +359,16 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       next_v();
       commit(&o_full[1]);
     }
-  } else if (warp < 8) {
-    // ===================== softmax warpgroups =====================
-    const int t = warp >> 2, quarter = warp & 3;
+  } else {
+    // ===================== softmax warps: thread = (query row, half of the key block) =====================
+    const int t = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
     const int r = quarter * 32 + lane;                                   // row inside the Q tile == TMEM lane
-    const uint32_t t_s = tmem_base + t * 128 + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t t_o = tmem_base + 256 + t * 128 + ((uint32_t)(quarter * 32) << 16);
-    uint32_t scnt = 0, itn = 0;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s = tmem_base + t * 128 + half * 64 + lane_off;     // my 64 S columns
+    const uint32_t t_p = tmem_base + t * 128 + half * 32 + lane_off;     // my 32 P columns (bf16x2; P aliases S columns 0..63)
+    const uint32_t t_o = tmem_base + 256 + t * 128 + half * 64 + lane_off;   // my 64 O columns
+    float* xch = reinterpret_cast<float*>(smem + Smem::xch) + t * 512;   // [parity][half][row]
+    uint32_t scnt = 0, itn = 0, xp = 0;
     const float c = p.scale_log2e;
     const uint64_t c2 = pack_f32x2(c, c);
     const int tail = p.Lk - (nb - 1) * BKEY;                             // valid keys in the last block (1..128)
@@ -390,15 +387,42 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         bar_wait(&s_full[t], scnt & 1);
         ++scnt;
         tcgen05_fence_after();
-        const int valid = (j == nb - 1) ? tail : BKEY;                   // keys of this block that exist
-        uint32_t sa[16], sb[16];                                         // S chunks 2g / 2g+1 live in sa / sb
-        uint32_t pk[16];                                                 // bf16x2 P of one chunk pair = 16 TMEM columns
-        tmem_ld_32x16(t_s, sa);
-#pragma unroll 1
-        for (int g = 0; g < 4; ++g) {
-          softmax_chunk<0>(sa, sb, pk, t_s, t_o, g, true, valid, j > 0, c, c2, m_ref, sum2);
-          softmax_chunk<1>(sb, sa, pk, t_s, t_o, g, g < 3, valid, j > 0, c, c2, m_ref, sum2);
-          tmem_st_32x16(t_s + g * 16, pk);                               // P columns alias S chunks already consumed
+        uint32_t sr[4][16];                                              // my half of the S row
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) tmem_ld_32x16(t_s + ch * 16, sr[ch]);
+        tmem_ld_wait();
+        if (j == nb - 1 && tail < BKEY) {                                // last, partial key block
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int e = 0; e < 16; ++e) if (half * 64 + ch * 16 + e >= tail) sr[ch][e] = 0xff800000u;   // -inf: P = 0
+        }
+        float hmax = __uint_as_float(sr[0][0]);
+#pragma unroll
+        for (int ch = 0; ch < 4; ++ch) hmax = max16(sr[ch], hmax);
+        // the two halves of a row agree on the block maximum; the barrier also orders "every S column of the tile is in
+        // registers" before "any P column (which aliases S columns 0..63) is written"
+        xch[xp * 256 + half * 128 + r] = hmax;
+        named_bar_sync(1 + t, 256);
+        const float bm = fmaxf(hmax, xch[xp * 256 + (half ^ 1) * 128 + r]) * c;   // c > 0
+        xp ^= 1;
+        const bool need = bm > m_ref + RESCALE_THRESHOLD;                // first block of an item: m_ref = -inf
+        if (__any_sync(0xffffffffu, need)) {
+          // ---- rare path: move the reference maximum; l and O accumulated against the old one are rescaled ----
+          const float m_new = need ? bm : m_ref;
+          const float alpha = ex2f(m_ref - m_new);                       // 0 from -inf, exactly 1 for rows that keep m_ref
+          sum2 = mul_f32x2(sum2, pack_f32x2(alpha, alpha));
+          if (j > 0) rescale_o(t_o, alpha);                              // S(j) complete implies P.V(j-1) complete
+          m_ref = m_new;
+        }
+        const float nm = -m_ref;
+        const uint64_t nm2 = pack_f32x2(nm, nm);
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          uint32_t pk[16];                                               // bf16x2 P of 32 keys = 16 TMEM columns
+          exp_chunk<POLY_PAIRS>(sr[2 * g], pk, c2, nm2, sum2);
+          exp_chunk<POLY_PAIRS>(sr[2 * g + 1], pk + 8, c2, nm2, sum2);
+          tmem_st_32x16(t_p + g * 16, pk);
         }
         tmem_st_wait();
         tcgen05_fence_before();
@@ -409,16 +433,19 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       // ---- read-out: out = O / l ----
       float s0, s1;
       unpack_f32x2(sum2, s0, s1);
-      const float l = s0 + s1;
+      xch[xp * 256 + half * 128 + r] = s0 + s1;
+      named_bar_sync(1 + t, 256);
+      const float l = (s0 + s1) + xch[xp * 256 + (half ^ 1) * 128 + r];
+      xp ^= 1;
       const float inv = 1.0f / l;
       bar_wait(&o_full[t], itn & 1);
       tcgen05_fence_after();
-      if (row_ok && p.lse_out != nullptr) p.lse_out[(long long)h * p.Lq + row] = m_ref + log2f(l);
-      __nv_bfloat16* g = p.out + (long long)(row_ok ? row : 0) * p.ldo + h * HD;
+      if (half == 0 && row_ok && p.lse_out != nullptr) p.lse_out[(long long)h * p.Lq + row] = m_ref + log2f(l);
+      __nv_bfloat16* g = p.out + (long long)(row_ok ? row : 0) * p.ldo + h * HD + half * 64;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
-        uint32_t o[32];
-        tmem_ld_32x32(t_o + ch * 32, o);
+        uint32_t o[16];
+        tmem_ld_32x16(t_o + ch * 16, o);
         tmem_ld_wait();
         if (ch == 3) {                                                   // O is in registers: hand the columns back
           tcgen05_fence_before();
@@ -427,13 +454,13 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         if (row_ok) {
 #pragma unroll
-          for (int e = 0; e < 32; e += 8) {
+          for (int e = 0; e < 16; e += 8) {
             uint4 w;
             w.x = pack_bf16x2(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv);
             w.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
             w.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
             w.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
-            *reinterpret_cast<uint4*>(g + ch * 32 + e) = w;
+            *reinterpret_cast<uint4*>(g + ch * 16 + e) = w;
           }
         }
       }
@@ -450,6 +477,14 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 }  // namespace b200q
 
 using namespace b200q;
+
+// scheduling knob (reserved: 0 = default schedule)
+static int g_fa_mode = 0;
+extern "C" int b200q_attn_bf16_set_mode(int mode) {
+  if (mode != 0) return B200Q_ERR_BAD_ARG;
+  g_fa_mode = mode;
+  return B200Q_OK;
+}
 
 extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
@@ -477,6 +512,7 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   p.n_qt = (int)((Lq + 2 * BQ - 1) / (2 * BQ));
   p.n_items = p.n_qt * num_heads;
   p.lse_out = lse_out;
+  p.mode = g_fa_mode;
   static bool configured = false;
   if (!configured) {
     B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
