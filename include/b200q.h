@@ -241,8 +241,9 @@ B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t
                     int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
                     float* lse_out, b200q_stream_t stream);
 
-/* Scheduling knob of b200q_attn_bf16 (debug / benchmarking; results identical): bit 0 = the softmax warpgroups of the two
- * query tiles take turns in their exponential sections instead of running concurrently. */
+/* Scheduling knob of b200q_attn_bf16 (debug / benchmarking): how many of every 8 element pairs of the softmax take the
+ * degree-4 polynomial exp2 on the FMA pipe instead of MUFU.EX2 (0..3, default 2 = 25 %; P within 7e-6 relative, far below
+ * its bf16 rounding). */
 B200Q_API int b200q_attn_bf16_set_mode(int mode);
 
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.

@@ -35,10 +35,17 @@ def main():
         g = torch.Generator(device="cuda").manual_seed(0)
         q, k, v = (torch.randn(L, H * 128, device=dev, generator=g).to(torch.bfloat16) for L in (Lq, Lk, Lk))
         flops = 4.0 * Lq * Lk * 128 * H
-        own = timed(lambda: b200q.attn_bf16(q, k, v, H), n)
-        lib = timed(lambda: M.sdpa(q, k, v, H), n)
+        # clocks drift under sustained load (power cap): interleave the variants and keep the minimum of three rounds
+        modes, lib = {}, 1e9
+        for _ in range(3):
+            for md in (2, 0, 1, 3):
+                b200q.attn_bf16_set_mode(md)
+                modes[md] = min(modes.get(md, 1e9), timed(lambda: b200q.attn_bf16(q, k, v, H), n))
+            lib = min(lib, timed(lambda: M.sdpa(q, k, v, H), n))
+        b200q.attn_bf16_set_mode(2)
+        own = modes[2]
         o1, o2 = b200q.attn_bf16(q, k, v, H).float(), M.sdpa(q, k, v, H).float()
-        res[name] = {"b200q_ms": own, "library_ms": lib, "b200q_tflops": flops / own / 1e9, "library_tflops": flops / lib / 1e9,
+        res[name] = {"b200q_ms": own, "by_poly_pairs_ms": modes, "library_ms": lib, "b200q_tflops": flops / own / 1e9, "library_tflops": flops / lib / 1e9,
                      "max_abs_diff": float((o1 - o2).abs().max())}
         print(name, json.dumps(res[name]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

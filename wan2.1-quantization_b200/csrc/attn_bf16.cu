@@ -204,16 +204,22 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sc)[16], uint32_t* pk
   }
 }
 
+__device__ __forceinline__ float max3(float a, float b, float c) {
+  float d;
+  asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));      // FMNMX3: one issue slot for two comparisons
+  return d;
+}
 __device__ __forceinline__ float max16(const uint32_t (&sc)[16], float m) {
   float m0 = m, m1 = m;
 #pragma unroll
   for (int e = 0; e < 16; e += 4) {
-    m0 = fmaxf(m0, fmaxf(__uint_as_float(sc[e]), __uint_as_float(sc[e + 1])));
-    m1 = fmaxf(m1, fmaxf(__uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3])));
+    m0 = max3(m0, __uint_as_float(sc[e]), __uint_as_float(sc[e + 1]));
+    m1 = max3(m1, __uint_as_float(sc[e + 2]), __uint_as_float(sc[e + 3]));
   }
   return fmaxf(m0, m1);
 }
 
+template <int POLY>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Params p) {
@@ -420,8 +426,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t pk[16];                                               // bf16x2 P of 32 keys = 16 TMEM columns
-          exp_chunk<POLY_PAIRS>(sr[2 * g], pk, c2, nm2, sum2);
-          exp_chunk<POLY_PAIRS>(sr[2 * g + 1], pk + 8, c2, nm2, sum2);
+          exp_chunk<POLY>(sr[2 * g], pk, c2, nm2, sum2);
+          exp_chunk<POLY>(sr[2 * g + 1], pk + 8, c2, nm2, sum2);
           tmem_st_32x16(t_p + g * 16, pk);
         }
         tmem_st_wait();
@@ -478,10 +484,10 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
 using namespace b200q;
 
-// scheduling knob (reserved: 0 = default schedule)
-static int g_fa_mode = 0;
+// scheduling knob: how many of every 8 element pairs take the polynomial exp2 instead of MUFU.EX2 (0..3; default 2 = 25 %)
+static int g_fa_mode = 2;
 extern "C" int b200q_attn_bf16_set_mode(int mode) {
-  if (mode != 0) return B200Q_ERR_BAD_ARG;
+  if (mode < 0 || mode > 3) return B200Q_ERR_BAD_ARG;
   g_fa_mode = mode;
   return B200Q_OK;
 }
@@ -515,11 +521,20 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   p.mode = g_fa_mode;
   static bool configured = false;
   if (!configured) {
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     configured = true;
   }
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
-  attn_bf16_kernel<<<grid, THREADS, Smem::total, (cudaStream_t)stream>>>(tq, tk, tv, p);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (g_fa_mode) {
+    case 0: attn_bf16_kernel<0><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    case 1: attn_bf16_kernel<1><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    case 3: attn_bf16_kernel<3><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    default: attn_bf16_kernel<2><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+  }
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
