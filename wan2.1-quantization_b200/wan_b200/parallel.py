@@ -124,32 +124,49 @@ class SequenceParallel:
         C = self.pipeline_chunks
         if C > 1 and Hg % C == 0:
             return self._attention_pipelined(q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C)
-        # pack per destination: [k | v | (q)] for the destination's head group
-        sends, recvs = [None] * P, [None] * P
-        for dst in range(P):
-            gd, hdst = dst % Pu, dst // Pu
-            cols = slice(gd * W, (gd + 1) * W)
-            parts = [k[:, cols], v[:, cols]]
-            if hdst == h:                              # my tokens' queries are served by replica h
-                parts.append(q[:, cols])
-            sends[dst] = torch.stack(parts, 0).contiguous()
-        for src in range(P):
-            n = 3 if (src // Pu) == h else 2
-            recvs[src] = torch.empty((n, Lr, W), dtype=q.dtype, device=q.device)
-        self._exchange(sends, recvs)
-        K = torch.cat([recvs[s][0] for s in range(P)], 0)                        # [L, W]
-        V = torch.cat([recvs[s][1] for s in range(P)], 0)
-        q_src = [s for s in range(P) if s // Pu == h]
-        Q = torch.cat([recvs[s][2] for s in q_src], 0)                           # [L/Pr, W]
-        O = core(Q, K, V, Hg)                                                    # [L/Pr, W]
+        # Group-major staging: x [Lr, Pu, W] -> [Pu, Lr, W], so the columns a destination needs are ONE contiguous chunk and
+        # every receive lands in place: K / V of all ranks as [P, Lr, W] == [L, W], Q of my replica as [Pu, Lr, W].  Three
+        # transposing copies in, one out, and two grouped NCCL send/recv batches per attention - instead of a stack per
+        # destination and a cat per tensor.
+        gm = lambda x: x.view(Lr, Pu, W).permute(1, 0, 2).contiguous()
+        qg, kg, vg = gm(q), gm(k), gm(v)
+        Kr = torch.empty((P, Lr, W), dtype=q.dtype, device=q.device)
+        Vr = torch.empty((P, Lr, W), dtype=q.dtype, device=q.device)
+        Qr = torch.empty((Pu, Lr, W), dtype=q.dtype, device=q.device)
+        ops = []
+        for peer in range(P):
+            gp, hp = peer % Pu, peer // Pu
+            if peer == self.rank:
+                Kr[peer].copy_(kg[gp]); Vr[peer].copy_(vg[gp]); Qr[gp].copy_(qg[gp])
+                continue
+            ops.append(dist.P2POp(dist.irecv, Kr[peer], self._global(peer), group=self.group))
+            ops.append(dist.P2POp(dist.irecv, Vr[peer], self._global(peer), group=self.group))
+            if hp == h:
+                ops.append(dist.P2POp(dist.irecv, Qr[gp], self._global(peer), group=self.group))
+            ops.append(dist.P2POp(dist.isend, kg[gp], self._global(peer), group=self.group))
+            ops.append(dist.P2POp(dist.isend, vg[gp], self._global(peer), group=self.group))
+            self.bytes_sent += 2 * kg[gp].numel() * kg.element_size()
+            if hp == h:                                # my tokens' queries are served by the ranks of my replica
+                ops.append(dist.P2POp(dist.isend, qg[gp], self._global(peer), group=self.group))
+                self.bytes_sent += qg[gp].numel() * qg.element_size()
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        O = core(Qr.view(Pu * Lr, W), Kr.view(P * Lr, W), Vr.view(P * Lr, W), Hg)   # [L/Pr, W]
         # return each token owner its rows of my head group
-        sends, recvs = [None] * P, [None] * P
-        for i, s in enumerate(q_src):
-            sends[s] = O[i * Lr:(i + 1) * Lr].contiguous()
-        for gsrc in range(Pu):                          # ranks (gsrc, h) computed my tokens
-            recvs[h * Pu + gsrc] = torch.empty((Lr, W), dtype=q.dtype, device=q.device)
-        self._exchange(sends, recvs)
-        return torch.cat([recvs[h * Pu + gsrc] for gsrc in range(Pu)], 1)        # [Lr, H*hd]
+        Or = torch.empty((Pu, Lr, W), dtype=O.dtype, device=O.device)
+        ops = []
+        for i in range(Pu):
+            peer = h * Pu + i                          # owner of query rows i*Lr .. (i+1)*Lr; it computed head group i for me
+            if peer == self.rank:
+                Or[i].copy_(O[i * Lr:(i + 1) * Lr])
+                continue
+            ops.append(dist.P2POp(dist.irecv, Or[i], self._global(peer), group=self.group))
+            ops.append(dist.P2POp(dist.isend, O[i * Lr:(i + 1) * Lr], self._global(peer), group=self.group))
+            self.bytes_sent += Lr * W * O.element_size()
+        if ops:
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+        return Or.permute(1, 0, 2).reshape(Lr, Pu * W)                          # [Lr, H*hd]
 
     def _attention_pipelined(self, q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C):
         """Head-chunked variant of attention(): chunk c of every head group travels as its own grouped send/recv; all

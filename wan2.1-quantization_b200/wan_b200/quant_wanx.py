@@ -1,8 +1,17 @@
-"""QuantWanMixin — the method surface of the reference's `QuantWanModel`
-(ViDiT-Q/examples/Wan2.1/wan/quant_wanx.py:28-228) for any module tree with WanModel's parameter names.
+"""QuantWanModel / QuantWanMixin — the reference's `QuantWanModel`
+(ViDiT-Q/examples/Wan2.1/wan/quant_wanx.py:28-228).
 
-The reference class subclasses its own `WanModel` (out of scope here and untouched); the quantization methods are plain
-tree surgery over `qdiff`, so they are provided as a mixin a maintainer composes with the reference model:
+`QuantWanModel` below is concrete: the mixin over `wan_b200.wan_model.WanModelFP` (a self-contained module tree with
+WanModel's parameter names, constructor arguments and call convention), with the reference's constructor signature
+(`quant_config=` keyword, :36-54) and `from_pretrained(ckpt_dir, quant_config=...)` (quant_generate.py:358-360), so the
+reference's sequence
+
+    model = QuantWanModel.from_pretrained(ckpt_dir, quant_config=cfg); model.quant_layer_refactor()
+    model.load_quant_param_dict(params); model.quantize_and_save_weight(path)
+    model.hardware_forward_refactor(load_path=path, seq_len=L); model.set_init_done(); model(x, t, context, seq_len)
+
+(quant_generate.py:355-420) runs against this package alone.  Where the reference's own `wan` package is importable the
+mixin composes with its model instead:
 
     from wan.modules.model import WanModel                      # the reference's model, unchanged
     from wan_b200.quant_wanx import QuantWanMixin
@@ -110,3 +119,20 @@ class QuantWanMixin:
             o = self._b200_step(u.float(), t[i:i + 1].float(), c)
             outs.append(o.clone() if len(x) > 1 else o)       # the graph's output buffer is reused by the next replay
         return outs
+
+
+from .wan_model import WanModelFP  # noqa: E402
+
+
+class QuantWanModel(QuantWanMixin, WanModelFP):
+    """quant_wanx.py:28-78: WanModel's constructor arguments plus `quant_config`; nothing is quantized until
+    `quant_layer_refactor()` / `convert_quant(cfg)` is called (the reference leaves that call to the caller as well, :75-76)."""
+
+    def __init__(self, model_type="t2v", patch_size=(1, 2, 2), text_len=512, in_dim=16, dim=1536, ffn_dim=8960, freq_dim=256,
+                 text_dim=4096, out_dim=16, num_heads=12, num_layers=30, window_size=(-1, -1), qk_norm=True,
+                 cross_attn_norm=True, eps=1e-6, quant_config=None):
+        super().__init__(model_type=model_type, patch_size=patch_size, text_len=text_len, in_dim=in_dim, dim=dim,
+                         ffn_dim=ffn_dim, freq_dim=freq_dim, text_dim=text_dim, out_dim=out_dim, num_heads=num_heads,
+                         num_layers=num_layers, window_size=window_size, qk_norm=qk_norm, cross_attn_norm=cross_attn_norm, eps=eps)
+        self.quant_config = quant_config
+        self.quant_param_dict = {}
