@@ -234,12 +234,18 @@ B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, 
  * head_dim^-0.5), no mask, no dropout; SDPA fallback :171-178): out = softmax(q.k^T * sm_scale) . v per head.
  *   q bf16 [Lq, H*128] (ldq), k, v bf16 [Lk, H*128] (ldk, ldv): row pitches in elements, multiples of 8, 16-byte aligned
  *   bases - column slices of a fused q|k|v GEMM output are fine.  out bf16 [Lq, H*128] (ldo).
- *   lse_out (optional, fp32 [H, Lq]): log2(sum_j 2^(x_ij)), x = q.k^T * sm_scale * log2(e), for merging key splits.
+ *   lse_out (optional, fp32 [H, Lq]): log2(sum_j 2^(x_ij)), x = q.k^T * sm_scale * log2(e) (n_splits == 1 only).
+ *   n_splits > 1: every (head, 256-query) work item is split along the keys into n_splits items (one persistent CTA per
+ *   SM walks the items, so more and shorter items fill the last wave; b200q_attn_bf16_splits proposes the count); the
+ *   partial outputs go to part_ws (bf16 [n_splits, Lq, H*128]) with their log-sum-exp in lse_ws (fp32 [n_splits, H, Lq]),
+ *   both caller-owned scratch, and a second launch merges them with the weights 2^(lse_s - lse).
  *   Q.K^T and P.V run as tcgen05.mma.kind::f16 with fp32 accumulators in TMEM, P is handed to the second product through
  *   tensor memory, V is consumed in its natural [keys, head_dim] layout; fp32 softmax statistics. */
 B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
-                    float* lse_out, b200q_stream_t stream);
+                    float* lse_out, int n_splits, void* part_ws, float* lse_ws, b200q_stream_t stream);
+/* Key-split count b200q_attn_bf16 should be called with for this shape on the current device (1 = no split). */
+B200Q_API int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads);
 
 /* Scheduling knob of b200q_attn_bf16 (debug / benchmarking): how many of every 8 element pairs of the softmax take the
  * degree-4 polynomial exp2 on the FMA pipe instead of MUFU.EX2 (0..3, default 2 = 25 %; P within 7e-6 relative, far below

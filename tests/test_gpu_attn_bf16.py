@@ -36,7 +36,7 @@ def test_attn_bf16_matches_fp32_softmax(dev, H, Lq, Lk):
     ref, lse_ref = _ref(q, k, v, H)
     _check(out, ref)
     assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
-    assert torch.equal(out, b200q.attn_bf16(q, k, v, H))            # deterministic
+    assert torch.equal(out, b200q.attn_bf16(q, k, v, H, n_splits=1))            # deterministic
 
 
 def test_attn_bf16_strided_operands_and_scale(dev):
@@ -104,3 +104,17 @@ def test_block_with_own_attention_core_matches_library_core(dev):
     finally:
         M.set_attention_core("library")
     _check(y_own, y_lib, tol=3e-2)
+
+
+@pytest.mark.parametrize("H,Lq,Lk,S", [(2, 300, 2500, 2), (3, 700, 4096 + 77, 3), (1, 256, 1024, 4), (2, 513, 1100, 8)])
+def test_attn_bf16_key_splits_merge(dev, H, Lq, Lk, S):
+    """work items split along the keys + log-sum-exp merge = the unsplit result up to bf16 rounding of the partials"""
+    g = torch.Generator(device="cuda").manual_seed(S * 100 + Lq)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g).to(torch.bfloat16) for n in (Lq, Lk, Lk))
+    out = b200q.attn_bf16(q, k, v, H, n_splits=S)
+    _check(out, _ref(q, k, v, H)[0])
+    one = b200q.attn_bf16(q, k, v, H, n_splits=1)
+    assert float((out.float() - one.float()).abs().max()) <= 2e-2 * float(one.float().abs().max())
+    # the library's own proposal is a valid count and small problems are left alone
+    assert b200q.load().b200q_attn_bf16_splits(Lq, Lk, H) in (1, 2, 3, 4)
+    assert b200q.load().b200q_attn_bf16_splits(64, 512, 2) == 1

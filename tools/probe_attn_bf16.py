@@ -28,7 +28,8 @@ def main():
     dev = torch.device("cuda")
     res = {}
     shapes = [("1.3B self H12 L32760", 12, 32760, 32760, 10), ("1.3B cross H12 L32760 x 512", 12, 32760, 512, 20),
-              ("1.3B/8 ranks H12 Lq4095", 12, 4095, 32760, 20), ("ulysses4 H3 L32760", 3, 32760, 32760, 10)]
+              ("1.3B/8 ranks Pu4xPr2: H3 Lq16380", 3, 16380, 32760, 20), ("ulysses4 H3 L32760", 3, 32760, 32760, 10),
+              ("ulysses2 H6 L32760", 6, 32760, 32760, 10)]
     if "--big" in sys.argv:
         shapes.append(("14B self H40 L75600", 40, 75600, 75600, 2))
     for name, H, Lq, Lk, n in shapes:
@@ -44,8 +45,10 @@ def main():
             lib = min(lib, timed(lambda: M.sdpa(q, k, v, H), n))
         b200q.attn_bf16_set_mode(2)
         own = modes[2]
+        nosplit = timed(lambda: b200q.attn_bf16(q, k, v, H, n_splits=1), n)
+        splits = b200q.load().b200q_attn_bf16_splits(Lq, Lk, H)
         o1, o2 = b200q.attn_bf16(q, k, v, H).float(), M.sdpa(q, k, v, H).float()
-        res[name] = {"b200q_ms": own, "by_poly_pairs_ms": modes, "library_ms": lib, "b200q_tflops": flops / own / 1e9, "library_tflops": flops / lib / 1e9,
+        res[name] = {"b200q_ms": own, "n_splits": splits, "unsplit_ms": nosplit, "by_poly_pairs_ms": modes, "library_ms": lib, "b200q_tflops": flops / own / 1e9, "library_tflops": flops / lib / 1e9,
                      "max_abs_diff": float((o1 - o2).abs().max())}
         print(name, json.dumps(res[name]), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)

@@ -65,7 +65,8 @@ _SIGNATURES = {
     "b200q_attn_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
-                                c_void_p, c_int64, c_void_p, c_void_p]),
+                                c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+    "b200q_attn_bf16_splits": (c_int, [c_int64, c_int64, c_int]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "b200q_had_quant_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
@@ -387,9 +388,15 @@ def quant_vt(v, n_bits=8):
     return buf[:, :Lk], delta
 
 
-def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False):
+# key splits of attn_bf16 when the caller does not say: None = the library's proposal per shape, 1 = never split (bit-identical
+# results for any sharding of the queries; bench.py --verify uses it)
+attn_bf16_default_splits = None
+
+
+def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_splits=None):
     """bf16 flash attention (include/b200q.h): q [Lq, H*128], k, v [Lk, H*128] bf16 (row-major, any row pitch that is a
-    multiple of 8 elements) -> bf16 [Lq, H*128]; want_lse=True also returns the fp32 [H, Lq] log2-sum-exp."""
+    multiple of 8 elements) -> bf16 [Lq, H*128]; want_lse=True also returns the fp32 [H, Lq] log2-sum-exp.
+    n_splits: key splits per work item (None = the library's proposal for this shape; 1 = none)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _cuda(t, n)
         if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
@@ -403,8 +410,16 @@ def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False):
     sm_scale = hd ** -0.5 if sm_scale is None else float(sm_scale)
     out = torch.empty((Lq, D), dtype=torch.bfloat16, device=q.device) if out is None else out
     lse = torch.empty((H, Lq), dtype=torch.float32, device=q.device) if want_lse else None
+    if n_splits is None:
+        n_splits = attn_bf16_default_splits
+    if n_splits is None:
+        n_splits = 1 if want_lse else load().b200q_attn_bf16_splits(Lq, Lk, H)
+    part = lse_ws = None
+    if n_splits > 1:
+        part = torch.empty((n_splits, Lq, D), dtype=torch.bfloat16, device=q.device)
+        lse_ws = torch.empty((n_splits, H, Lq), dtype=torch.float32, device=q.device)
     rc = load().b200q_attn_bf16(_ptr(q), _ld(q), _ptr(k), _ld(k), _ptr(v), _ld(v), Lq, Lk, H, hd, sm_scale, _ptr(out), _ld(out),
-                                _ptr(lse), _stream())
+                                _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _stream())
     _check(rc, "b200q_attn_bf16")
     return (out, lse) if want_lse else out
 

@@ -62,6 +62,8 @@ struct Params {
   __nv_bfloat16* out; long long ldo;
   float scale_log2e;
   int n_items, n_qt;
+  int n_splits, bps;             // key splits per (head, query-tile pair) item and key blocks per split
+  long long split_stride;        // elements between the partial outputs of consecutive splits (n_splits > 1)
   int mode;                      // scheduling knob (b200q_attn_bf16_set_mode)
   float* lse_out;                // optional [H, Lq]: log2(sum_j 2^(x_j)) per row, for key-split merges
 };
@@ -242,7 +244,9 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int nb = (p.Lk + BKEY - 1) / BKEY;
+  const int nb_all = (p.Lk + BKEY - 1) / BKEY;
+  // item -> (head, key split, query-tile pair); a split covers key blocks [kb0, kb0 + nb)
+  const int per_head = p.n_qt * p.n_splits;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
@@ -267,7 +271,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     if (lane == 0) {
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
-        const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
+        const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
+        const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
         bar_wait(q_empty, (it & 1) ^ 1);
         mbar_expect_tx(q_full, 2 * TILE);
 #pragma unroll
@@ -278,13 +283,13 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         for (int j = 0; j < nb; ++j) {
           bar_wait(&k_empty[ks], kph ^ 1);
           mbar_expect_tx(&k_full[ks], TILE);
-          tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, j * BKEY);
-          tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, j * BKEY);
+          tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, (kb0 + j) * BKEY);
+          tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, (kb0 + j) * BKEY);
           if (++ks == KS) { ks = 0; kph ^= 1; }
           bar_wait(&v_empty[vs], vph ^ 1);
           mbar_expect_tx(&v_full[vs], TILE);
-          tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, j * BKEY);
-          tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, j * BKEY);
+          tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, (kb0 + j) * BKEY);
+          tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, (kb0 + j) * BKEY);
           if (++vs == VS) { vs = 0; vph ^= 1; }
         }
       }
@@ -337,6 +342,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     auto next_k = [&]() { commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
     auto next_v = [&]() { commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      const int nb = min(p.bps, nb_all - ((item % per_head) / p.n_qt) * p.bps);
       bar_wait(q_full, it & 1);
       bar_wait(&k_full[ks], kph);
       tcgen05_fence_after();
@@ -377,14 +383,15 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     uint32_t scnt = 0, itn = 0, xp = 0;
     const float c = p.scale_log2e;
     const uint64_t c2 = pack_f32x2(c, c);
-    const int tail = p.Lk - (nb - 1) * BKEY;                             // valid keys in the last block (1..128)
+    const int tail = p.Lk - (nb_all - 1) * BKEY;                         // valid keys in the last block (1..128)
     {                                                                    // O columns start out free
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[t]);
     }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
-      const int h = item / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
+      const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
+      const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
       const int row = q0 + r;
       const bool row_ok = row < p.Lq;
       float m_ref = -INFINITY;                                           // reference maximum of the exponentials (log2 units)
@@ -397,7 +404,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) tmem_ld_32x16(t_s + ch * 16, sr[ch]);
         tmem_ld_wait();
-        if (j == nb - 1 && tail < BKEY) {                                // last, partial key block
+        if (kb0 + j == nb_all - 1 && tail < BKEY) {                      // last, partial key block
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
 #pragma unroll
@@ -446,8 +453,8 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const float inv = 1.0f / l;
       bar_wait(&o_full[t], itn & 1);
       tcgen05_fence_after();
-      if (half == 0 && row_ok && p.lse_out != nullptr) p.lse_out[(long long)h * p.Lq + row] = m_ref + log2f(l);
-      __nv_bfloat16* g = p.out + (long long)(row_ok ? row : 0) * p.ldo + h * HD + half * 64;
+      if (half == 0 && row_ok && p.lse_out != nullptr) p.lse_out[((long long)sp * p.H + h) * p.Lq + row] = m_ref + log2f(l);
+      __nv_bfloat16* g = p.out + sp * p.split_stride + (long long)(row_ok ? row : 0) * p.ldo + h * HD + half * 64;
 #pragma unroll
       for (int ch = 0; ch < 4; ++ch) {
         uint32_t o[16];
@@ -479,6 +486,35 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == W_TMA) tmem_dealloc<512>(tmem_base);
 }
 
+// Key-split merge: out[row, c] = sum_s w_s * part[s][row, c] / sum_s w_s,  w_s = 2^(lse[s][h][row] - max_s lse) - the
+// flash-attention split-K identity.  Thread = 8 columns of one row.
+__global__ void __launch_bounds__(256) attn_merge_kernel(const __nv_bfloat16* __restrict__ part, long long split_stride, int ld_part,
+                                                         const float* __restrict__ lse, int n_splits, int Lq, int H,
+                                                         __nv_bfloat16* __restrict__ out, long long ldo) {
+  const int vec_per_row = H * HD / 8;
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (long long)Lq * vec_per_row) return;
+  const int row = (int)(i / vec_per_row), c = (int)(i % vec_per_row) * 8, h = c / HD;
+  float w[8], m = -INFINITY, tot = 0.f;
+  for (int s = 0; s < n_splits; ++s) { w[s] = lse[((long long)s * H + h) * Lq + row]; m = fmaxf(m, w[s]); }
+  for (int s = 0; s < n_splits; ++s) { w[s] = ex2f(w[s] - m); tot += w[s]; }
+  const float inv = 1.0f / tot;
+  float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  for (int s = 0; s < n_splits; ++s) {
+    const uint4 v = *reinterpret_cast<const uint4*>(part + s * split_stride + (long long)row * ld_part + c);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    const float ws = w[s] * inv;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[2 * e] = fmaf(__uint_as_float(u[e] << 16), ws, acc[2 * e]);
+      acc[2 * e + 1] = fmaf(__uint_as_float(u[e] & 0xffff0000u), ws, acc[2 * e + 1]);
+    }
+  }
+  uint4 o;
+  o.x = pack_bf16x2(acc[0], acc[1]); o.y = pack_bf16x2(acc[2], acc[3]); o.z = pack_bf16x2(acc[4], acc[5]); o.w = pack_bf16x2(acc[6], acc[7]);
+  *reinterpret_cast<uint4*>(out + (long long)row * ldo + c) = o;
+}
+
 }  // namespace fa
 }  // namespace b200q
 
@@ -492,9 +528,28 @@ extern "C" int b200q_attn_bf16_set_mode(int mode) {
   return B200Q_OK;
 }
 
+// How many key splits b200q_attn_bf16 should use for this shape (1 = none): (head, query-tile pair) items are walked by one
+// persistent CTA per SM, so a grid that is not a multiple of the SM count leaves a partial last wave; splitting the keys
+// multiplies the item count and shortens each item.  cost(S) = waves(S) * (key blocks per split + fixed per-item overhead).
+extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
+  using namespace fa;
+  if (Lq <= 0 || Lk <= 0 || num_heads <= 0) return 1;
+  const long long items = ((Lq + 2 * BQ - 1) / (2 * BQ)) * num_heads;
+  const int nb = (int)((Lk + BKEY - 1) / BKEY), sms = sm_count();
+  int best = 1;
+  double best_cost = 0;
+  for (int S = 1; S <= 4; ++S) {
+    if (S > 1 && nb / S < 8) break;                                   // keep splits long enough to amortise prologue / read-out
+    const int bps = (nb + S - 1) / S, s_eff = (nb + bps - 1) / bps;
+    const double cost = (double)((items * s_eff + sms - 1) / sms) * (bps + 3.0) + (S > 1 ? 0.02 * (nb + 3.0) * ((items + sms - 1) / sms) : 0.0);
+    if (S == 1 || cost < best_cost * 0.97) { if (S == 1 || cost < best_cost) { best = s_eff; best_cost = cost; } }
+  }
+  return best;
+}
+
 extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
-                               float* lse_out, b200q_stream_t stream) {
+                               float* lse_out, int n_splits, void* part_ws, float* lse_ws, b200q_stream_t stream) {
   clear_error();
   using namespace fa;
   B200Q_REQUIRE(q && k && v && out, B200Q_ERR_BAD_ARG, "attn_bf16: null pointer");
@@ -516,8 +571,20 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   p.out = (__nv_bfloat16*)out; p.ldo = ldo;
   p.scale_log2e = sm_scale * 1.4426950408889634f;
   p.n_qt = (int)((Lq + 2 * BQ - 1) / (2 * BQ));
-  p.n_items = p.n_qt * num_heads;
-  p.lse_out = lse_out;
+  const int nb_all = (int)((Lk + BKEY - 1) / BKEY);
+  if (n_splits < 1) n_splits = 1;
+  if (n_splits > 8) n_splits = 8;
+  p.bps = (nb_all + n_splits - 1) / n_splits;
+  p.n_splits = (nb_all + p.bps - 1) / p.bps;                          // every split non-empty
+  if (p.n_splits > 1) {
+    B200Q_REQUIRE(part_ws && lse_ws && aligned(part_ws, 16), B200Q_ERR_BAD_ARG,
+                  "attn_bf16: n_splits > 1 needs part_ws (bf16 [n_splits, Lq, heads*128]) and lse_ws (fp32 [n_splits, heads, Lq])");
+    B200Q_REQUIRE(lse_out == nullptr, B200Q_ERR_UNSUPPORTED, "attn_bf16: lse_out is only available without key splits");
+    p.out = (__nv_bfloat16*)part_ws; p.ldo = D; p.split_stride = Lq * D; p.lse_out = lse_ws;
+  } else {
+    p.split_stride = 0; p.lse_out = lse_out;
+  }
+  p.n_items = p.n_qt * num_heads * p.n_splits;
   p.mode = g_fa_mode;
   static bool configured = false;
   if (!configured) {
@@ -536,5 +603,11 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
     default: attn_bf16_kernel<2><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
   }
   B200Q_CHECK_LAUNCH();
+  if (p.n_splits > 1) {
+    const long long vecs = Lq * (D / 8);
+    attn_merge_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)part_ws, p.split_stride, (int)D, lse_ws,
+                                                                    p.n_splits, (int)Lq, num_heads, (__nv_bfloat16*)out, ldo);
+    B200Q_CHECK_LAUNCH();
+  }
   return B200Q_OK;
 }

@@ -169,48 +169,60 @@ class SequenceParallel:
         return Or.permute(1, 0, 2).reshape(Lr, Pu * W)                          # [Lr, H*hd]
 
     def _attention_pipelined(self, q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C):
-        """Head-chunked variant of attention(): chunk c of every head group travels as its own grouped send/recv; all
-        inbound exchanges are posted up front, each chunk's attention waits only for its own operands, and its output
-        is sent back while the next chunk is being computed."""
+        """Head-chunked variant of attention(): the heads of a group travel and are attended in C chunks.  Staging layout
+        [Pu, C, Lr, Wc] makes every (destination group, chunk) one contiguous message; all inbound exchanges are posted up
+        front (NCCL runs them back to back on its own stream), each chunk's attention waits only for its own operands, and
+        its output travels back while the next chunk is being computed."""
         P = self.world_size
         Hc = Hg // C
-        Wc, W = Hc * hd, Hg * hd
-        q_src = [s for s in range(P) if s // Pu == h]
+        Wc = Hc * hd
+        gm = lambda x: x.view(Lr, Pu, C, Wc).permute(1, 2, 0, 3).contiguous()
+        qg, kg, vg = gm(q), gm(k), gm(v)
+        Kr = torch.empty((C, P, Lr, Wc), dtype=q.dtype, device=q.device)
+        Vr = torch.empty((C, P, Lr, Wc), dtype=q.dtype, device=q.device)
+        Qr = torch.empty((C, Pu, Lr, Wc), dtype=q.dtype, device=q.device)
         inbound = []
         for c in range(C):
-            sends, recvs = [None] * P, [None] * P
-            for dst in range(P):
-                gd, hdst = dst % Pu, dst // Pu
-                cols = slice(gd * W + c * Wc, gd * W + (c + 1) * Wc)
-                parts = [k[:, cols], v[:, cols]]
-                if hdst == h:
-                    parts.append(q[:, cols])
-                sends[dst] = torch.stack(parts, 0).contiguous()
-            for src in range(P):
-                n = 3 if (src // Pu) == h else 2
-                recvs[src] = torch.empty((n, Lr, Wc), dtype=q.dtype, device=q.device)
-            inbound.append((self._exchange_async(sends, recvs), recvs, sends))
-        outbound, out_recvs = [], []
+            ops = []
+            for peer in range(P):
+                gp, hp = peer % Pu, peer // Pu
+                if peer == self.rank:
+                    Kr[c, peer].copy_(kg[gp, c]); Vr[c, peer].copy_(vg[gp, c]); Qr[c, gp].copy_(qg[gp, c])
+                    continue
+                ops.append(dist.P2POp(dist.irecv, Kr[c, peer], self._global(peer), group=self.group))
+                ops.append(dist.P2POp(dist.irecv, Vr[c, peer], self._global(peer), group=self.group))
+                if hp == h:
+                    ops.append(dist.P2POp(dist.irecv, Qr[c, gp], self._global(peer), group=self.group))
+                ops.append(dist.P2POp(dist.isend, kg[gp, c], self._global(peer), group=self.group))
+                ops.append(dist.P2POp(dist.isend, vg[gp, c], self._global(peer), group=self.group))
+                self.bytes_sent += 2 * Lr * Wc * q.element_size()
+                if hp == h:
+                    ops.append(dist.P2POp(dist.isend, qg[gp, c], self._global(peer), group=self.group))
+                    self.bytes_sent += Lr * Wc * q.element_size()
+            inbound.append(dist.batch_isend_irecv(ops) if ops else [])
+        Or = torch.empty((Pu, Lr, C, Wc), dtype=q.dtype, device=q.device)        # [group, row, chunk, Wc] == [Pu, Lr, W]
+        outbound, keep = [], []
         for c in range(C):
-            works, recvs, _keep = inbound[c]
-            for w in works:
+            for w in inbound[c]:
                 w.wait()
-            K = torch.cat([recvs[s][0] for s in range(P)], 0)
-            V = torch.cat([recvs[s][1] for s in range(P)], 0)
-            Q = torch.cat([recvs[s][2] for s in q_src], 0)
-            O = core(Q, K, V, Hc)                                                  # [L/Pr, Wc]
-            sends, recvs_o = [None] * P, [None] * P
-            for i, s in enumerate(q_src):
-                sends[s] = O[i * Lr:(i + 1) * Lr].contiguous()
-            for gsrc in range(Pu):
-                recvs_o[h * Pu + gsrc] = torch.empty((Lr, Wc), dtype=q.dtype, device=q.device)
-            outbound.append((self._exchange_async(sends, recvs_o), sends))
-            out_recvs.append(recvs_o)
-        for works, _keep in outbound:
-            for w in works:
+            O = core(Qr[c].view(Pu * Lr, Wc), Kr[c].view(P * Lr, Wc), Vr[c].view(P * Lr, Wc), Hc)   # [L/Pr, Wc]
+            Oc = torch.empty((Pu, Lr, Wc), dtype=O.dtype, device=O.device)       # what the peers computed for my rows
+            ops = []
+            for i in range(Pu):
+                peer = h * Pu + i
+                if peer == self.rank:
+                    Oc[i].copy_(O[i * Lr:(i + 1) * Lr])
+                    continue
+                ops.append(dist.P2POp(dist.irecv, Oc[i], self._global(peer), group=self.group))
+                ops.append(dist.P2POp(dist.isend, O[i * Lr:(i + 1) * Lr], self._global(peer), group=self.group))
+                self.bytes_sent += Lr * Wc * O.element_size()
+            outbound.append(dist.batch_isend_irecv(ops) if ops else [])
+            keep.append((O, Oc))
+        for c in range(C):
+            for w in outbound[c]:
                 w.wait()
-        # column order of the result: head group gsrc, then chunk c inside the group
-        return torch.cat([out_recvs[c][h * Pu + gsrc] for gsrc in range(Pu) for c in range(C)], 1)
+            Or[:, :, c].copy_(keep[c][1])
+        return Or.permute(1, 0, 2, 3).reshape(Lr, Pu * C * Wc)                   # [Lr, H*hd]: group, chunk, head-in-chunk
 
     # ---- calibration ---------------------------------------------------------------------------------------------
     def allreduce_max(self, flat_stats):
