@@ -1,0 +1,14 @@
+#!/bin/bash
+# Round-2 GPU batch: parity tests, the headline bench, the ncu launch list of the step and one --set full capture of
+# every hot kernel.  Results under gpurun_out/ (tools/summarize_ncu.py turns them into profiles/).
+set -u
+cd "$(dirname "$0")/.."
+mkdir -p gpurun_out
+TAG=${TAG:-r2}
+timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
+timeout 600 python tools/run_kernels.py > gpurun_out/${TAG}_run_kernels.log 2>&1; echo "run_kernels rc=$?"
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}.csv \
+  python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-variants > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
+timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
+  -o gpurun_out/prof_${TAG} -f python tools/run_kernels.py > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"

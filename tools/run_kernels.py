@@ -1,4 +1,5 @@
-"""Short driver for ncu captures: launches each hot kernel a few times at the BASELINE shapes (1.3B, L=32760)."""
+"""Short driver for ncu captures: every hot kernel at the BASELINE shapes (1.3B, L=32760).  Two warm passes, then ONE pass
+between cudaProfilerStart/Stop:  ncu --profile-from-start off --set full ... python tools/run_kernels.py"""
 import os
 import sys
 
@@ -31,24 +32,39 @@ bd, bf = torch.rand(D, device=dev), torch.rand(Fd, device=dev)
 res = torch.randn(L, D, device=dev)
 qkv = torch.randn(L, 3 * D, device=dev, dtype=torch.bfloat16)
 cos = torch.rand(L, 64, device=dev); sin = torch.rand(L, 64, device=dev)
-for _ in range(3):
+sys.path.insert(0, os.path.join(ROOT, "wan2.1-quantization_b200"))
+from qdiff.base.quant_layer import ActPlan  # noqa: E402
+plan = ActPlan.rotation(D, torch.ones(D), torch.rand(D) + 0.5, dev)
+H = 12
+qb, kb, vb = (torch.randn(L, D, device=dev).to(torch.bfloat16) for _ in range(3))
+
+
+def one_pass():
     b200q.quant_rows(x32, 8, True, True)
     b200q.quant_rows(h16, 8, True, True)
     b200q.calib_update(x32, stat)
     b200q.ln_mod_quant(x32, 1e-6, None, None, sh, sh, 8)
     b200q.rmsnorm_rope(qkv[:, :D], dwd, 1e-6, cos, sin, 128)
+    b200q.had_quant_rows(x32, plan.colscale, plan.hadK, plan.K, plan.log2w, 8)          # f-2: smooth scale + Hadamard + quant
     b200q.gemm_w8a8(qa, w_dd, da, dwd, zd, rs, bd)                                             # D->D, bf16 out
     b200q.gemm_w8a8(qa, w_fd, da, dwf, zf, rs, bf, epilogue=b200q.EPI_GELU_TANH)               # D->F + GELU
     b200q.gemm_w8a8(qh, w_df, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # F->D
     b200q.gemm_w8a8(qa, w_dd, da, dwd, zd, rs, bd, epilogue=b200q.EPI_GATE_RESIDUAL, residual=res, gate=sh)   # D->D gate
     b200q.gemm_w4a8(qa, w4, D, da, dwf, zf, rs, bf)
     b200q.gemm_w8a8(qa, w_qkv, da, dwq, zq, rs, bq)                                            # D->3D (q|k|v), bf16 out
-# quantized attention path (configs[4]): fused Q/K quantizer, V^T quantizer, int8 attention (H=12, L=32760)
-H = 12
-for _ in range(2):
+    b200q.attn_bf16(qb, kb, vb, H)                                                             # attention core of configs[1]
+    # quantized attention path (configs[4]): fused Q/K quantizer, V^T quantizer, int8 attention (H=12, L=32760)
     qq, dq, _ = b200q.rmsnorm_rope_quant(qkv[:, :D], dwd, 1e-6, cos, sin, 128)
     kq, dk, _ = b200q.rmsnorm_rope_quant(qkv[:, D:2 * D], dwd, 1e-6, cos, sin, 128)
     vt, dv = b200q.quant_vt(qkv[:, 2 * D:], 8)
     b200q.attn_i8(qq, dq, kq, dk, vt, dv, H)
+
+
+for _ in range(2):
+    one_pass()
 torch.cuda.synchronize()
+torch.cuda.profiler.start()
+one_pass()
+torch.cuda.synchronize()
+torch.cuda.profiler.stop()
 print("ok", b200q.launch_count)

@@ -59,7 +59,9 @@ __device__ __forceinline__ float row_reduce_max(float v, float* s_slot, int warp
 
 // MODE bit 0: LayerNorm affine (ln_w, ln_b) ; bit 1: adaLN modulate (scale, shift).  Compile-time so the inner loops
 // carry no per-element selects.  All element math is packed fp32x2 (FADD2 / FMUL2 / FFMA2).
-template <typename T, typename YT, int V, int THREADS, int MODE>
+// FULL: cols == V * warps_per_row * 32 vectors exactly, so every lane holds live data whenever its row exists and the
+// per-vector predicates, selects and index clamps disappear (the Wan dims: 1536 = 12 x 32 float4, 5120 = 10 x 128).
+template <typename T, typename YT, int V, int THREADS, int MODE, bool FULL>
 __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, const int warps_per_row) {
   using VT = Vec16<T>;
   constexpr int N = VT::N;
@@ -86,7 +88,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   uint64_t acc2 = pack_f32x2(0.f, 0.f);
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    live[v] = row_ok && (v * tpr + t) < kv;
+    live[v] = FULL ? row_ok : (row_ok && (v * tpr + t) < kv);
     const uint4 raw = live[v] ? ldg_stream16(xrow + (int64_t)v * tpr * N) : make_uint4(0, 0, 0, 0);
     VT::unpack_pairs(raw, x[v]);
 #pragma unroll
@@ -101,7 +103,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   for (int v = 0; v < V; ++v) {
 #pragma unroll
     for (int i = 0; i < P; ++i) {
-      x[v][i] = live[v] ? add_f32x2(x[v][i], nmean2) : pack_f32x2(0.f, 0.f);       // d = x - mean (0 for padding lanes)
+      x[v][i] = (FULL || live[v]) ? add_f32x2(x[v][i], nmean2) : pack_f32x2(0.f, 0.f);   // d = x - mean (0 for padding lanes)
       ss2 = fma_f32x2(x[v][i], x[v][i], ss2);
     }
   }
@@ -113,7 +115,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
   float amax = 0.f;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
-    const int c0 = live[v] ? (v * tpr + t) * N : 0;
+    const int c0 = (FULL || live[v]) ? (v * tpr + t) * N : 0;
 #pragma unroll
     for (int h = 0; h < N / 4; ++h) {
       uint64_t y0 = mul_f32x2(x[v][2 * h], rstd2), y1 = mul_f32x2(x[v][2 * h + 1], rstd2);
@@ -129,7 +131,7 @@ __global__ void __launch_bounds__(THREADS) ln_mod_quant_kernel(const LnArgs a, c
         y0 = add_f32x2(mul_f32x2(y0, add_f32x2(one2, pack_f32x2(s4.x, s4.y))), pack_f32x2(h4.x, h4.y));
         y1 = add_f32x2(mul_f32x2(y1, add_f32x2(one2, pack_f32x2(s4.z, s4.w))), pack_f32x2(h4.z, h4.w));
       }
-      if (!live[v]) { y0 = pack_f32x2(0.f, 0.f); y1 = y0; }
+      if (!FULL && !live[v]) { y0 = pack_f32x2(0.f, 0.f); y1 = y0; }
       x[v][2 * h] = y0; x[v][2 * h + 1] = y1;
       float f0, f1, f2, f3;
       unpack_f32x2(y0, f0, f1); unpack_f32x2(y1, f2, f3);
@@ -210,11 +212,19 @@ static int launch_ln_mode(const LnArgs& a, cudaStream_t st) {
                 (long long)a.cols);
   const int rows_per_cta = (lay.threads / 32) / W;
   const unsigned grid = (unsigned)((a.rows + rows_per_cta - 1) / rows_per_cta);
-  if (lay.threads == 1024) ln_mod_quant_kernel<T, YT, 8, 1024, MODE><<<grid, 1024, 0, st>>>(a, W);
-  else if (V <= 2) ln_mod_quant_kernel<T, YT, 2, 256, MODE><<<grid, 256, 0, st>>>(a, W);
-  else if (V <= 4) ln_mod_quant_kernel<T, YT, 4, 256, MODE><<<grid, 256, 0, st>>>(a, W);
-  else if (V <= 8) ln_mod_quant_kernel<T, YT, 8, 256, MODE><<<grid, 256, 0, st>>>(a, W);
-  else ln_mod_quant_kernel<T, YT, 12, 256, MODE><<<grid, 256, 0, st>>>(a, W);
+  const bool full = (kv == V * W * 32);
+#define B200Q_LN(VV, TH)                                                                              \
+  do {                                                                                                \
+    if (full && V == (VV)) ln_mod_quant_kernel<T, YT, VV, TH, MODE, true><<<grid, TH, 0, st>>>(a, W);  \
+    else ln_mod_quant_kernel<T, YT, VV, TH, MODE, false><<<grid, TH, 0, st>>>(a, W);                   \
+  } while (0)
+  if (lay.threads == 1024) B200Q_LN(8, 1024);
+  else if (V <= 2) B200Q_LN(2, 256);
+  else if (V <= 4) B200Q_LN(4, 256);
+  else if (V <= 8) B200Q_LN(8, 256);
+  else if (V <= 10) B200Q_LN(10, 256);
+  else B200Q_LN(12, 256);
+#undef B200Q_LN
   B200Q_CHECK_LAUNCH();
   return B200Q_OK;
 }
