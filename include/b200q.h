@@ -239,11 +239,16 @@ B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, 
  *   SM walks the items, so more and shorter items fill the last wave; b200q_attn_bf16_splits proposes the count); the
  *   partial outputs go to part_ws (bf16 [n_splits, Lq, H*128]) with their log-sum-exp in lse_ws (fp32 [n_splits, H, Lq]),
  *   both caller-owned scratch, and a second launch merges them with the weights 2^(lse_s - lse).
+ *   qk_norm_ws (optional, fp32 [2, H] caller-owned scratch): when given, a first launch takes the per-head maxima of the
+ *   row norms of q and k; heads whose scores are bounded by Cauchy-Schwarz, max|q_i| max|k_j| sm_scale log2(e) <= 80, run a
+ *   max-free softmax (P = 2^x without a running maximum: bf16 / fp32 have the exponent range, and a float's relative
+ *   precision does not depend on its magnitude - same function, fewer instructions, no rescaling); all other heads run the
+ *   online-softmax kernel.  null = online softmax for every head.
  *   Q.K^T and P.V run as tcgen05.mma.kind::f16 with fp32 accumulators in TMEM, P is handed to the second product through
  *   tensor memory, V is consumed in its natural [keys, head_dim] layout; fp32 softmax statistics. */
 B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
-                    float* lse_out, int n_splits, void* part_ws, float* lse_ws, b200q_stream_t stream);
+                    float* lse_out, int n_splits, void* part_ws, float* lse_ws, float* qk_norm_ws, b200q_stream_t stream);
 /* Key-split count b200q_attn_bf16 should be called with for this shape on the current device (1 = no split). */
 B200Q_API int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads);
 
@@ -251,6 +256,9 @@ B200Q_API int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads);
  * degree-4 polynomial exp2 on the FMA pipe instead of MUFU.EX2 (0..3, default 2 = 25 %; P within 7e-6 relative, far below
  * its bf16 rounding). */
 B200Q_API int b200q_attn_bf16_set_mode(int mode);
+/* Max-free kernel of b200q_attn_bf16 (bounded heads): polynomial pairs of every 8 (0..5, default 3 - the fastest under the
+ * power cap: 5.48 ms at H=12, L=32760 sustained, against 6.31 ms for the online softmax); -1 disables the max-free kernel (every head takes the online softmax even when qk_norm_ws is given). */
+B200Q_API int b200q_attn_bf16_set_fast(int poly_pairs);
 
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the

@@ -118,3 +118,53 @@ def test_attn_bf16_key_splits_merge(dev, H, Lq, Lk, S):
     # the library's own proposal is a valid count and small problems are left alone
     assert b200q.load().b200q_attn_bf16_splits(Lq, Lk, H) in (1, 2, 3, 4)
     assert b200q.load().b200q_attn_bf16_splits(64, 512, 2) == 1
+
+
+def test_attn_bf16_bounded_and_unbounded_heads_in_one_call(dev):
+    """head classes (include/b200q.h qk_norm_ws): head 0 has small norms (Cauchy-Schwarz bound <= 80 -> max-free kernel),
+    head 1 has keys scaled far beyond it (online-softmax kernel), head 2 sits just above the bound; one call, every head
+    must match fp32 softmax attention, with and without key splits"""
+    H, Lq, Lk = 3, 700, 1300
+    g = torch.Generator(device="cuda").manual_seed(21)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g) for n in (Lq, Lk, Lk))
+    k[:, 128:256] *= 12.0
+    k[:, 256:] *= 3.5
+    q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    ref, lse_ref = _ref(q, k, v, H)
+    out, lse = b200q.attn_bf16(q, k, v, H, want_lse=True)
+    _check(out, ref, tol=3e-2)
+    assert torch.allclose(lse, lse_ref, atol=5e-3, rtol=1e-4)
+    _check(b200q.attn_bf16(q, k, v, H, n_splits=3), ref, tol=3e-2)
+
+
+@pytest.mark.parametrize("poly", [2, 3, 4, 5])
+def test_attn_bf16_max_free_kernel_equals_online_softmax(dev, poly):
+    """the max-free kernel (bounded heads) and the online-softmax kernel compute the same function: compare them on the
+    same inputs for every polynomial share, full and partial last key block, rows beyond Lq"""
+    H, Lq, Lk = 4, 1000, 2100
+    g = torch.Generator(device="cuda").manual_seed(poly)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g).to(torch.bfloat16) for n in (Lq, Lk, Lk))
+    try:
+        b200q.attn_bf16_set_fast(-1)
+        online, lse_o = b200q.attn_bf16(q, k, v, H, want_lse=True)
+        b200q.attn_bf16_set_fast(poly)
+        fast, lse_f = b200q.attn_bf16(q, k, v, H, want_lse=True)
+    finally:
+        b200q.attn_bf16_set_fast(3)
+    ref, lse_ref = _ref(q, k, v, H)
+    _check(fast, ref)
+    _check(online, ref)
+    assert float((fast.float() - online.float()).abs().max()) <= 1e-2 * float(ref.abs().max())
+    assert torch.allclose(lse_f, lse_ref, atol=2e-3, rtol=1e-4) and torch.allclose(lse_o, lse_ref, atol=2e-3, rtol=1e-4)
+
+
+def test_attn_bf16_nan_and_huge_inputs_take_the_online_kernel(dev):
+    """a head with an enormous key norm must not overflow in the max-free kernel: it is classified unbounded"""
+    H, Lq, Lk = 2, 256, 512
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g) for n in (Lq, Lk, Lk))
+    k[100, :128] *= 300.0                                           # one giant key in head 0
+    q, k, v = q.to(torch.bfloat16), k.to(torch.bfloat16), v.to(torch.bfloat16)
+    out = b200q.attn_bf16(q, k, v, H)
+    assert torch.isfinite(out.float()).all()
+    _check(out, _ref(q, k, v, H)[0], tol=3e-2)

@@ -10,5 +10,11 @@ timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 
 timeout 600 python tools/run_kernels.py > gpurun_out/${TAG}_run_kernels.log 2>&1; echo "run_kernels rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}.csv \
   python bench.py --layers 2 --steps 1 --warmup 3 --no-cpu-baseline --no-graph --no-variants > gpurun_out/${TAG}_ncu_list.log 2>&1; echo "ncu list rc=$?"
-timeout 1200 ncu --set full --clock-control none --import-source on --profile-from-start off \
-  -o gpurun_out/prof_${TAG} -f python tools/run_kernels.py > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+# the report of ~25 kernels with source exceeds what gpurun brings back (64 MiB): keep it on the box, bring the raw page as CSV
+timeout 1200 ncu --set full --clock-control none --profile-from-start off -o /tmp/prof_${TAG} -f python tools/run_kernels.py \
+  > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
+ncu -i /tmp/prof_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null; ls -la /tmp/prof_${TAG}.ncu-rep gpurun_out/prof_${TAG}_raw.csv
+# attention core alone, with source (small report)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bf16_kernel --launch-skip 2 -c 1 -o gpurun_out/fa_${TAG} -f \
+  python tools/run_attn_bf16.py 12 32760 32760 3 > gpurun_out/${TAG}_ncu_fa.log 2>&1; echo "ncu fa rc=$?"
+du -sh gpurun_out

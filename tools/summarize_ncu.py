@@ -29,8 +29,12 @@ WANT = [
     ("smsp__inst_executed.sum", "warp insts"),
 ]
 
-if os.path.exists(rep):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = os.path.join(ROOT, "gpurun_out", f"prof_{tag}_raw.csv")       # written on the GPU box when the report is too big to travel
+if os.path.exists(rep) or os.path.exists(raw_csv):
+    if os.path.exists(rep):
+        raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    else:
+        raw = open(raw_csv).read()
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(hdr)}
@@ -60,6 +64,11 @@ if os.path.exists(rep):
     attn_rows = [r for r in rows[2:] if "attn_i8_kernel" in r[col["Kernel Name"]]]
     if attn_rows:
         traffic["attn_i8_H12_L32760"] = to_bytes(attn_rows[0], "dram__bytes_read.sum") + to_bytes(attn_rows[0], "dram__bytes_write.sum")
+    for key, pat in (("attn_bf16_H12_L32760", "attn_bf16_kernel"), ("ln_mod_quant_32760x1536", "ln_mod_quant_kernel"),
+                     ("rmsnorm_rope_32760x1536", "rmsnorm_rope_kernel"), ("had_quant_rows_32760x1536", "had_")):
+        rr = [r for r in rows[2:] if pat in r[col["Kernel Name"]]]
+        if rr:
+            traffic[key] = to_bytes(rr[0], "dram__bytes_read.sum") + to_bytes(rr[0], "dram__bytes_write.sum")
     json.dump(traffic, open(os.path.join(out_dir, "traffic.json"), "w"), indent=1)
     print("wrote traffic.json", traffic["gemm"])
 

@@ -65,7 +65,8 @@ _SIGNATURES = {
     "b200q_attn_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
-                                c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
+                                c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200q_attn_bf16_set_fast": (c_int, [c_int]),
     "b200q_attn_bf16_splits": (c_int, [c_int64, c_int64, c_int]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
@@ -391,6 +392,7 @@ def quant_vt(v, n_bits=8):
 # key splits of attn_bf16 when the caller does not say: None = the library's proposal per shape, 1 = never split (bit-identical
 # results for any sharding of the queries; bench.py --verify uses it)
 attn_bf16_default_splits = None
+attn_bf16_bounded_heads = True      # classify heads by the Cauchy-Schwarz score bound and run bounded heads max-free
 
 
 def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_splits=None):
@@ -414,14 +416,21 @@ def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_spl
         n_splits = attn_bf16_default_splits
     if n_splits is None:
         n_splits = 1 if want_lse else load().b200q_attn_bf16_splits(Lq, Lk, H)
+    norm_ws = torch.empty(2 * H, dtype=torch.float32, device=q.device) if attn_bf16_bounded_heads else None
     part = lse_ws = None
     if n_splits > 1:
         part = torch.empty((n_splits, Lq, D), dtype=torch.bfloat16, device=q.device)
         lse_ws = torch.empty((n_splits, H, Lq), dtype=torch.float32, device=q.device)
     rc = load().b200q_attn_bf16(_ptr(q), _ld(q), _ptr(k), _ld(k), _ptr(v), _ld(v), Lq, Lk, H, hd, sm_scale, _ptr(out), _ld(out),
-                                _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _stream())
+                                _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _ptr(norm_ws), _stream())
     _check(rc, "b200q_attn_bf16")
     return (out, lse) if want_lse else out
+
+
+def attn_bf16_set_fast(poly_pairs):
+    """polynomial pairs of every 8 in the max-free kernel (2..5); -1 = online softmax for every head"""
+    if load().b200q_attn_bf16_set_fast(int(poly_pairs)) != 0:
+        raise B200QError("b200q_attn_bf16_set_fast: bad value")
 
 
 def attn_bf16_set_mode(mode):

@@ -17,7 +17,8 @@ OBJ_DIR = os.path.join(LIB_DIR, "obj")
 LIB = os.path.join(LIB_DIR, "libb200q.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"] + \
+        os.environ.get("B200Q_NVCC_EXTRA", "").split()          # e.g. -DB200Q_FA_TRACE (diagnostic builds only)
 
 
 def sources():
@@ -53,7 +54,7 @@ def build(force=False, verbose=False):
                     sys.stderr.write(r.stdout + r.stderr)
                 if r.returncode != 0:
                     raise RuntimeError(f"nvcc failed on {name}")
-    if jobs or not os.path.exists(LIB):
+    if jobs or not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(o) for o in objs):
         cmd = [NVCC, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-cudart", "shared"]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:

@@ -45,7 +45,6 @@ constexpr int TILE = 2 * HALF;              // a 128 x 128 bf16 operand tile = t
 constexpr int KS = 2, VS = 2;
 constexpr int THREADS = 18 * 32;             // 16 softmax warps + TMA producer + MMA issuer
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
-constexpr int POLY_PAIRS = 2;               // of every 8 element pairs, this many take the polynomial exp2 (25 %)
 
 struct Smem {
   static constexpr int q = 0;                       // 2 tiles
@@ -66,7 +65,22 @@ struct Params {
   long long split_stride;        // elements between the partial outputs of consecutive splits (n_splits > 1)
   int mode;                      // scheduling knob (b200q_attn_bf16_set_mode)
   float* lse_out;                // optional [H, Lq]: log2(sum_j 2^(x_j)) per row, for key-split merges
+  const float* qk_norm;          // optional [2, H]: max over rows of |q_i|^2 / |k_j|^2 of the head's slices (attn_qk_norm_kernel)
 };
+
+// Bounded-score heads: |S_ij * scale * log2(e)| <= |q_i| |k_j| scale log2(e) <= B (Cauchy-Schwarz on the per-head maxima of
+// the row norms).  For B <= FAST_BOUND the exponentials 2^x need no running maximum at all: P = 2^x lies in
+// [2^-80, 2^80], the fp32 row sum below 2^(80+31) and the fp32 O accumulator below 2^(80+31) |v|_max - bf16 and fp32 have
+// the exponent range, and the relative precision of a float does not depend on its magnitude.  Such heads take the
+// max-free kernel (no row maximum, no exchange between the two threads of a row, no rescaling, S consumed in two
+// streamed halves); every other head takes the online-softmax kernel.  Both kernels walk the same item list and skip the
+// heads of the other class.
+constexpr float FAST_BOUND = 80.0f;
+__device__ __forceinline__ bool head_is_bounded(const Params& p, int h) {
+  if (p.qk_norm == nullptr) return false;
+  const float b = sqrtf(p.qk_norm[h] * p.qk_norm[p.H + h]) * fabsf(p.scale_log2e);   // qk_norm holds squared norms
+  return b <= FAST_BOUND;                                                 // false for NaN / inf
+}
 
 // kind::f16 instruction descriptor: D = fp32, A = B = bf16, A K-major; B K-major (Q.K^T) or MN-major (P.V)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major) {
@@ -145,6 +159,22 @@ __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
   }
 }
 
+// Critical-path waits (S ready / P ready): selectable polling flavour, b200q_attn_bf16_set_mode bits 64 / 128.
+//   0: try_wait with a 20 us suspend hint (fewest issue slots)   64: try_wait, default time limit   128: test_wait spin
+__device__ __forceinline__ void bar_wait_crit(uint64_t* bar, uint32_t parity, int mode) {
+  if ((mode & 192) == 0) { bar_wait(bar, parity); return; }
+  const uint32_t addr = smem_u32(bar);
+  uint32_t done = 0, spins = 0;
+  while (true) {
+    if (mode & 128)
+      asm volatile("{\n.reg .pred P1;\nmbarrier.test_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    else
+      asm volatile("{\n.reg .pred P1;\nmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\nselp.u32 %0, 1, 0, P1;\n}\n" : "=r"(done) : "r"(addr), "r"(parity) : "memory");
+    if (done) return;
+    if (++spins > 400000000u) __trap();
+  }
+}
+
 // Rare path of the lazy rescaling: multiply this thread's 64 columns of the O accumulator row by alpha (rolled loop: runs
 // a handful of times per row).
 __device__ __forceinline__ void rescale_o(uint32_t t_o, float alpha) {
@@ -206,6 +236,43 @@ __device__ __forceinline__ void exp_chunk(const uint32_t (&sc)[16], uint32_t* pk
   }
 }
 
+// Max-free variant (bounded heads): P = 2^(S*c) for one 16-key chunk, |S*c| <= FAST_BOUND.  POLY of the 8 pairs take a
+// degree-3 polynomial on the FMA pipe (max relative error 7.5e-5, bf16 rounds P to 3.9e-3): t = S*c + 1.5*2^23 puts
+// n = rne(S*c) into the low mantissa bits, r = S*c - n by a second FFMA2, 2^n by an integer multiply-add into the exponent
+// field - 8 issue slots per pair against 3 (FFMA2 + 2 MUFU) on the MUFU path, and no clamp because the range is known.
+template <int POLY>
+__device__ __forceinline__ void exp_chunk_fast(const uint32_t (&sc)[16], uint32_t* pk, uint64_t c2, uint64_t& sum2) {
+  const uint64_t magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+#pragma unroll
+  for (int e = 0; e < 16; e += 2) {
+    const uint64_t s2 = pack_u32x2(sc[e], sc[e + 1]);
+    uint64_t p2;
+    // the polynomial pairs are spread over the chunk so that neither pipe sees a burst
+    constexpr uint32_t kPolyMask[9] = {0x00, 0x01, 0x11, 0x49, 0x55, 0x57, 0x77, 0x7F, 0xFF};
+    if ((kPolyMask[POLY] >> (e >> 1)) & 1u) {
+      const uint64_t t = fma_f32x2(s2, c2, magic2);
+      const uint64_t nn = fma_f32x2(t, pack_f32x2(-1.f, -1.f), magic2);                      // -n
+      const uint64_t r = fma_f32x2(s2, c2, nn);                                              // r = S*c - n in [-0.5, 0.5]
+      uint64_t q = fma_f32x2(r, pack_f32x2(0.0551716685295105f, 0.0551716685295105f), pack_f32x2(0.2426111251115799f, 0.2426111251115799f));
+      q = fma_f32x2(q, r, pack_f32x2(0.6932609677314758f, 0.6932609677314758f));
+      q = fma_f32x2(q, r, pack_f32x2(0.9999280571937561f, 0.9999280571937561f));
+      uint32_t q0, q1, t0, t1;
+      unpack_u32x2(q, q0, q1);
+      unpack_u32x2(t, t0, t1);
+      p2 = pack_u32x2(q0 + (t0 << 23), q1 + (t1 << 23));
+    } else {
+      const uint64_t x2 = mul_f32x2(s2, c2);
+      float x0, x1;
+      unpack_f32x2(x2, x0, x1);
+      p2 = pack_f32x2(ex2f(x0), ex2f(x1));
+    }
+    sum2 = add_f32x2(sum2, p2);
+    float p0, p1;
+    unpack_f32x2(p2, p0, p1);
+    pk[e >> 1] = pack_bf16x2(p0, p1);
+  }
+}
+
 __device__ __forceinline__ float max3(float a, float b, float c) {
   float d;
   asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));      // FMNMX3: one issue slot for two comparisons
@@ -221,7 +288,17 @@ __device__ __forceinline__ float max16(const uint32_t (&sc)[16], float m) {
   return fmaxf(m0, m1);
 }
 
-template <int POLY>
+// Diagnostic build (-DB200Q_FA_TRACE): CTA 0 prints, per warp role, the cycles spent in each phase of its first item.
+#ifdef B200Q_FA_TRACE
+__device__ __forceinline__ long long tr_clock() { long long c; asm volatile("mov.u64 %0, %%clock64;" : "=l"(c)::"memory"); return c; }
+#define TR_DECL long long tr_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}
+#define TR(i) do { if (j == 100) tr_acc[i] = tr_clock(); } while (0)     /* absolute time stamps of key block 100 */
+#else
+#define TR_DECL
+#define TR(i)
+#endif
+
+template <int POLY, bool FAST>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Params p) {
@@ -270,10 +347,12 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
+        if (head_is_bounded(p, h) != FAST) continue;                      // the other kernel's head
         const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
         bar_wait(q_empty, (it & 1) ^ 1);
+        ++it;
         mbar_expect_tx(q_full, 2 * TILE);
 #pragma unroll
         for (int t = 0; t < 2; ++t)
@@ -312,10 +391,12 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       const uint64_t b0 = kd + (uint64_t)(stage * (TILE >> 4));
       const uint32_t d = tmem_base + t * 128;
       if (elect_one()) {
+        if (!(p.mode & 16)) {
 #pragma unroll
-        for (int kk = 0; kk < HD / 16; ++kk) {
-          const uint64_t off = (uint64_t)((kk >> 2) * (HALF >> 4) + (kk & 3) * 2);
-          mma_bf16_ss(d, a0 + off, b0 + off, idesc_qk, kk != 0 ? 1u : 0u);
+          for (int kk = 0; kk < HD / 16; ++kk) {
+            const uint64_t off = (uint64_t)((kk >> 2) * (HALF >> 4) + (kk & 3) * 2);
+            mma_bf16_ss(d, a0 + off, b0 + off, idesc_qk, kk != 0 ? 1u : 0u);
+          }
         }
         mma_commit(&s_full[t]);
       }
@@ -323,15 +404,18 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     };
     // O[t] (+)= P_t (TMEM, bf16 packed in the S columns) . V(stage) : 8 x (M128, N128, K16); 16 keys = 2048 B of the V tile
     auto pv = [&](int t, int stage, bool first) {
-      if (t == 0) { bar_wait(&p_full[0], pcnt0 & 1); ++pcnt0; } else { bar_wait(&p_full[1], pcnt1 & 1); ++pcnt1; }
+      if (t == 0) { bar_wait_crit(&p_full[0], pcnt0 & 1, p.mode); ++pcnt0; } else { bar_wait_crit(&p_full[1], pcnt1 & 1, p.mode); ++pcnt1; }
       tcgen05_fence_after();
       const uint64_t b0 = vd + (uint64_t)(stage * (TILE >> 4));
       const uint32_t d = tmem_base + 256 + t * 128;
       const uint32_t pa = tmem_base + t * 128;
-      if (elect_one()) {
+      if (elect_one() && !(p.mode & 16)) {
+        // P columns: the online-softmax kernel packs the row's 128 keys into S columns 0..63; the max-free kernel leaves
+        // each half-row thread's 64 keys in the first 32 of ITS OWN 64 S columns (no cross-thread hazard, no barrier)
 #pragma unroll
         for (int kk = 0; kk < BKEY / 16; ++kk)
-          mma_bf16_ts(d, pa + kk * 8, b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (first && kk == 0) ? 0u : 1u);
+          mma_bf16_ts(d, pa + (FAST ? (kk >> 2) * 64 + (kk & 3) * 8 : kk * 8), b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv,
+                      (first && kk == 0) ? 0u : 1u);
       }
       __syncwarp();
     };
@@ -342,7 +426,9 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     auto next_k = [&]() { commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
     auto next_v = [&]() { commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+      if (head_is_bounded(p, item / per_head) != FAST) { --it; continue; }
       const int nb = min(p.bps, nb_all - ((item % per_head) / p.n_qt) * p.bps);
+      TR_DECL;
       bar_wait(q_full, it & 1);
       bar_wait(&k_full[ks], kph);
       tcgen05_fence_after();
@@ -353,17 +439,29 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       bar_wait(&v_full[vs], vph);
       pv(0, vs, true);
       for (int j = 1; j < nb; ++j) {
+        TR(0);
         bar_wait(&k_full[ks], kph);
+        TR(1);
         tcgen05_fence_after();
         qk(0, ks);                                           // S0(j): in order behind P0.V(j-1), which read P0 = S0's columns
         if (j == 1) bar_wait(&o_free[1], it & 1);
+        TR(2);
         pv(1, vs, j == 1);                                   // P1.V(j-1)
+        TR(3);
         next_v();
         qk(1, ks);                                           // S1(j)
         next_k();
+        TR(4);
         bar_wait(&v_full[vs], vph);
+        TR(5);
         pv(0, vs, false);                                    // P0.V(j)
+        TR(6);
       }
+#ifdef B200Q_FA_TRACE
+      if (blockIdx.x == 0 && it == 0 && lane == 0)
+        printf("MMA  j=100 stamps: top %lld  k_ready %lld  S0_issued %lld  PV1_issued %lld  S1_issued %lld  v_ready %lld  PV0_issued %lld\n",
+               tr_acc[0] % 10000000, tr_acc[1] % 10000000, tr_acc[2] % 10000000, tr_acc[3] % 10000000, tr_acc[4] % 10000000, tr_acc[5] % 10000000, tr_acc[6] % 10000000);
+#endif
       commit(&o_full[0]);
       commit(q_empty);                                       // last read of the Q tiles was S1(nb-1)
       if (nb == 1) bar_wait(&o_free[1], it & 1);
@@ -391,19 +489,78 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     }
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
       const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
+      if (head_is_bounded(p, h) != FAST) { --itn; continue; }
       const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
       const int row = q0 + r;
       const bool row_ok = row < p.Lq;
-      float m_ref = -INFINITY;                                           // reference maximum of the exponentials (log2 units)
+      float m_ref = FAST ? 0.f : -INFINITY;                              // reference maximum of the exponentials (log2 units)
       uint64_t sum2 = pack_f32x2(0.f, 0.f);
-      for (int j = 0; j < nb; ++j) {
-        bar_wait(&s_full[t], scnt & 1);
+      TR_DECL;
+      for (int j = 0; FAST && j < nb; ++j) {
+        // ---- max-free softmax of a bounded head: P = 2^(S*c), streamed in two 32-column halves ----
+        TR(0);
+        bar_wait_crit(&s_full[t], scnt & 1, p.mode);
+        TR(1);
         ++scnt;
         tcgen05_fence_after();
+        const uint32_t t_pf = t_s;                                       // P goes into the first 32 of my own 64 S columns
+        uint32_t sa[2][16], sb[2][16];
+        tmem_ld_32x16(t_s, sa[0]);
+        tmem_ld_32x16(t_s + 16, sa[1]);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 32, sb[0]);                                  // in flight during the first half's exponentials
+        tmem_ld_32x16(t_s + 48, sb[1]);
+        TR(2);
+        uint32_t pk[16];
+        if (kb0 + j == nb_all - 1 && tail < BKEY) {                      // last, partial key block: -inf -> MUFU path gives P = 0
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (half * 64 + e >= tail) sa[0][e] = 0xff800000u;
+            if (half * 64 + 16 + e >= tail) sa[1][e] = 0xff800000u;
+            if (half * 64 + 32 + e >= tail) sb[0][e] = 0xff800000u;
+            if (half * 64 + 48 + e >= tail) sb[1][e] = 0xff800000u;
+          }
+          exp_chunk_fast<0>(sa[0], pk, c2, sum2);
+          exp_chunk_fast<0>(sa[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_pf, pk);
+          exp_chunk_fast<0>(sb[0], pk, c2, sum2);
+          exp_chunk_fast<0>(sb[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_pf + 16, pk);
+        } else {
+          exp_chunk_fast<POLY>(sa[0], pk, c2, sum2);
+          exp_chunk_fast<POLY>(sa[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_pf, pk);
+          tmem_ld_wait();
+          TR(3);
+          exp_chunk_fast<POLY>(sb[0], pk, c2, sum2);
+          exp_chunk_fast<POLY>(sb[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_pf + 16, pk);
+        }
+        TR(5);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&p_full[t]);
+        TR(6);
+      }
+      for (int j = 0; !FAST && j < nb; ++j) {
+        TR(0);
+        bar_wait_crit(&s_full[t], scnt & 1, p.mode);
+        TR(1);
+        ++scnt;
+        tcgen05_fence_after();
+        if (p.mode & 8) {                                                // diagnostic: tensor / TMA pipeline alone
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          continue;
+        }
         uint32_t sr[4][16];                                              // my half of the S row
 #pragma unroll
         for (int ch = 0; ch < 4; ++ch) tmem_ld_32x16(t_s + ch * 16, sr[ch]);
         tmem_ld_wait();
+        TR(2);
         if (kb0 + j == nb_all - 1 && tail < BKEY) {                      // last, partial key block
 #pragma unroll
           for (int ch = 0; ch < 4; ++ch)
@@ -416,8 +573,10 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         // the two halves of a row agree on the block maximum; the barrier also orders "every S column of the tile is in
         // registers" before "any P column (which aliases S columns 0..63) is written"
         xch[xp * 256 + half * 128 + r] = hmax;
+        TR(3);
         named_bar_sync(1 + t, 256);
         const float bm = fmaxf(hmax, xch[xp * 256 + (half ^ 1) * 128 + r]) * c;   // c > 0
+        TR(4);
         xp ^= 1;
         const bool need = bm > m_ref + RESCALE_THRESHOLD;                // first block of an item: m_ref = -inf
         if (__any_sync(0xffffffffu, need)) {
@@ -430,6 +589,13 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         }
         const float nm = -m_ref;
         const uint64_t nm2 = pack_f32x2(nm, nm);
+        if (p.mode & 32) {                                               // diagnostic: TMEM load + row maximum + exchange only
+          if (nm == 12345.f) tmem_st_32x16(t_p, sr[0]);
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&p_full[t]);
+          continue;
+        }
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
           uint32_t pk[16];                                               // bf16x2 P of 32 keys = 16 TMEM columns
@@ -437,11 +603,18 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           exp_chunk<POLY>(sr[2 * g + 1], pk + 8, c2, nm2, sum2);
           tmem_st_32x16(t_p + g * 16, pk);
         }
+        TR(5);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&p_full[t]);
+        TR(6);
       }
+#ifdef B200Q_FA_TRACE
+      if (blockIdx.x == 0 && itn == 0 && lane == 0 && (warp & 3) == 0)
+        printf("SM w%02d j=100 stamps: top %lld  S_ready %lld  ld_done %lld  t3 %lld  t4 %lld  exp_issued %lld  arrived %lld\n",
+               warp, tr_acc[0] % 10000000, tr_acc[1] % 10000000, tr_acc[2] % 10000000, tr_acc[3] % 10000000, tr_acc[4] % 10000000, tr_acc[5] % 10000000, tr_acc[6] % 10000000);
+#endif
 
       // ---- read-out: out = O / l ----
       float s0, s1;
@@ -486,6 +659,45 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == W_TMA) tmem_dealloc<512>(tmem_base);
 }
 
+// Per-head maxima of the squared row norms: norms[h] = max_i |q_i,h|^2 (blockIdx.y = h), norms[H + h] = max_j |k_j,h|^2
+// (blockIdx.y = H + h).  16 lanes read one 256-byte head slice of a row (16 B each); one atomicMax per CTA (the values
+// are non-negative, so the integer order of the bit patterns is the float order).  norms must be zeroed before.
+__global__ void __launch_bounds__(256) attn_qk_norm_kernel(const __nv_bfloat16* __restrict__ q, long long ldq, int Lq,
+                                                           const __nv_bfloat16* __restrict__ k, long long ldk, int Lk, int H,
+                                                           float* __restrict__ norms) {
+  const bool is_k = (int)blockIdx.y >= H;
+  const int h = is_k ? (int)blockIdx.y - H : (int)blockIdx.y;
+  const __nv_bfloat16* base = (is_k ? k : q) + h * HD;
+  const long long ld = is_k ? ldk : ldq;
+  const int L = is_k ? Lk : Lq;
+  const int grp = threadIdx.x >> 4, l16 = threadIdx.x & 15;
+  const uint32_t hmask = 0xffffu << (threadIdx.x & 16);                   // the two row groups of a warp may leave the loop apart
+  float best = 0.f;
+  for (int row = blockIdx.x * 16 + grp; row < L; row += gridDim.x * 16) {
+    const uint4 v = ldg_stream16(base + (long long)row * ld + l16 * 8);
+    const uint32_t u[4] = {v.x, v.y, v.z, v.w};
+    float ss = 0.f;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float a = __uint_as_float(u[e] << 16), b = __uint_as_float(u[e] & 0xffff0000u);
+      ss = fmaf(a, a, fmaf(b, b, ss));
+    }
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) ss += __shfl_xor_sync(hmask, ss, o, 16);
+    best = fmaxf(best, ss);                                               // NaN rows: see below
+    if (ss != ss) best = INFINITY;                                        // NaN input -> unbounded -> online-softmax kernel
+  }
+  __shared__ float s_best[16];
+  if (l16 == 0) s_best[grp] = best;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float m = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) m = fmaxf(m, s_best[i]);
+    atomicMax(reinterpret_cast<int*>(norms + blockIdx.y), __float_as_int(m));
+  }
+}
+
 // Key-split merge: out[row, c] = sum_s w_s * part[s][row, c] / sum_s w_s,  w_s = 2^(lse[s][h][row] - max_s lse) - the
 // flash-attention split-K identity.  Thread = 8 columns of one row.
 __global__ void __launch_bounds__(256) attn_merge_kernel(const __nv_bfloat16* __restrict__ part, long long split_stride, int ld_part,
@@ -520,11 +732,20 @@ __global__ void __launch_bounds__(256) attn_merge_kernel(const __nv_bfloat16* __
 
 using namespace b200q;
 
-// scheduling knob: how many of every 8 element pairs take the polynomial exp2 instead of MUFU.EX2 (0..3; default 2 = 25 %)
+// scheduling knob: how many of every 8 element pairs take the polynomial exp2 instead of MUFU.EX2 (0..3; default 2 = 25 %).
+// Diagnostic bits (results are then meaningless; timing probes only): +8 = softmax warps hand S straight back (the tensor /
+// TMA / shared-memory pipeline alone), +16 = the MMA warp walks its schedule without issuing (the softmax warps alone),
+// +32 = softmax warps stop after the TMEM load, row maximum and exchange.
 static int g_fa_mode = 2;
+static int g_fa_fast_poly = 3;      // max-free kernel: polynomial pairs of every 8 (0..5); -1 = never use the max-free kernel
 extern "C" int b200q_attn_bf16_set_mode(int mode) {
-  if (mode < 0 || mode > 3) return B200Q_ERR_BAD_ARG;
+  if (mode < 0 || mode > 255 || (mode & 4)) return B200Q_ERR_BAD_ARG;
   g_fa_mode = mode;
+  return B200Q_OK;
+}
+extern "C" int b200q_attn_bf16_set_fast(int poly_pairs) {
+  if (poly_pairs < -1 || poly_pairs > 5) return B200Q_ERR_BAD_ARG;
+  g_fa_fast_poly = poly_pairs;
   return B200Q_OK;
 }
 
@@ -549,7 +770,8 @@ extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
 
 extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
-                               float* lse_out, int n_splits, void* part_ws, float* lse_ws, b200q_stream_t stream) {
+                               float* lse_out, int n_splits, void* part_ws, float* lse_ws, float* qk_norm_ws,
+                               b200q_stream_t stream) {
   clear_error();
   using namespace fa;
   B200Q_REQUIRE(q && k && v && out, B200Q_ERR_BAD_ARG, "attn_bf16: null pointer");
@@ -586,21 +808,45 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   }
   p.n_items = p.n_qt * num_heads * p.n_splits;
   p.mode = g_fa_mode;
+  p.qk_norm = (g_fa_fast_poly >= 0) ? qk_norm_ws : nullptr;
   static bool configured = false;
   if (!configured) {
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
     configured = true;
   }
   const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   cudaStream_t st = (cudaStream_t)stream;
-  switch (g_fa_mode) {
-    case 0: attn_bf16_kernel<0><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 1: attn_bf16_kernel<1><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 3: attn_bf16_kernel<3><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    default: attn_bf16_kernel<2><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+  if (p.qk_norm != nullptr) {
+    // classify the heads (bounded scores -> max-free kernel), then run both kernels over the item list: each skips the
+    // other's heads, so a launch whose class is empty costs a few microseconds
+    B200Q_CUDA_OK(cudaMemsetAsync(qk_norm_ws, 0, sizeof(float) * 2 * num_heads, st));
+    attn_qk_norm_kernel<<<dim3(64, 2 * num_heads), 256, 0, st>>>((const __nv_bfloat16*)q, ldq, (int)Lq, (const __nv_bfloat16*)k, ldk,
+                                                                 (int)Lk, num_heads, qk_norm_ws);
+    B200Q_CHECK_LAUNCH();
+    switch (g_fa_fast_poly) {
+      case 0: attn_bf16_kernel<0, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+      case 1: attn_bf16_kernel<1, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+      case 2: attn_bf16_kernel<2, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+      case 5: attn_bf16_kernel<5, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+      case 4: attn_bf16_kernel<4, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+      default: attn_bf16_kernel<3, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    }
+    B200Q_CHECK_LAUNCH();
+  }
+  switch (g_fa_mode & 3) {
+    case 0: attn_bf16_kernel<0, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    case 1: attn_bf16_kernel<1, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    case 3: attn_bf16_kernel<3, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
+    default: attn_bf16_kernel<2, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
   }
   B200Q_CHECK_LAUNCH();
   if (p.n_splits > 1) {
