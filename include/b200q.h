@@ -149,13 +149,17 @@ B200Q_API int b200q_pack_w4(const int8_t* codes, int64_t ld, int64_t N, int64_t 
  *  kernels/csrc/qgemm/w4a8/w4a8_per_channel_gemm_cuda_qserve.cu:304-656).
  * qw4 [N, ceil(K/8)*4] uint8 (ldw4 bytes, multiple of 16).  The packed tile travels by TMA; four converter warps expand
  * it to an int8 SWIZZLE_128B tile in shared memory before the MMA.  rowsum_a is REQUIRED (nibble bias); with
- * out_dtype B200Q_I32 the raw accumulators are sum_k qa*(code+8). */
+ * out_dtype B200Q_I32 the raw accumulators are sum_k qa*(code+8).
+ * expand_ws (optional caller scratch, N * ceil(K/32)*32 bytes, 16-byte aligned): when given and M >= 1024 the packed
+ * matrix is expanded once per call to one byte per code (microseconds: the weights are N*K/2 bytes) and the product runs
+ * on the W8A8 kernel - in the DiT every one of the M/128 row tiles would otherwise repeat the same expansion in shared
+ * memory.  Same accumulators, same epilogue algebra (zp_eff = zp_w - 8); the weights stay 4-bit in HBM and in checkpoints. */
 B200Q_API int b200q_gemm_w4a8(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4,
                     const float* delta_a, const float* delta_w, const float* zp_w,
                     const int32_t* rowsum_a, const void* bias, int bias_dtype,
                     void* out, int out_dtype, int64_t ldo,
                     int64_t M, int64_t N, int64_t K,
-                    int epilogue, const float* residual, int64_t ldr, const float* gate,
+                    int epilogue, const float* residual, int64_t ldr, const float* gate, void* expand_ws,
                     b200q_stream_t stream);
 
 /* ---- fused token-local operators (next-row f-1) ----------------------------------------

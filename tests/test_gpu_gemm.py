@@ -252,3 +252,37 @@ def test_cluster_modes_bit_exact(dev, M, N, K, mode):
         assert float((x.cpu().double() - (res.double() + y * gate.double())).abs().max()) <= 1e-3 * float(y.abs().max() + 1)
     finally:
         b200q.gemm_set_cluster(0)
+
+
+@pytest.mark.parametrize("M,N,K", [(1500, 512, 1536), (2100, 304, 1008), (1024, 1536, 8960)])
+def test_w4a8_expanded_weights_path_equals_in_kernel_converter(dev, M, N, K):
+    """M >= 1024 (include/b200q.h expand_ws): the packed weights are expanded once per call and the product runs on the
+    W8A8 kernel with the nibble bias folded through the zero point - bit-identical to the in-kernel converter path, for
+    every epilogue, incl. a K that is a multiple of 16 but not of 32, and asymmetric weights."""
+    g = torch.Generator().manual_seed(M + K)
+    qa, qw = _codes(M, K, 31), _codes(N, K, 32, -8, 7)
+    da = (torch.rand(M, generator=g) * 0.01 + 0.005).to(dev)
+    dw = (torch.rand(N, generator=g) * 0.1 + 0.1).to(dev)
+    zp = torch.randint(-3, 4, (N,), generator=g).float().to(dev)
+    bias = torch.randn(N, generator=g).to(dev)
+    rs = qa.to(torch.int32).sum(dim=1).to(torch.int32).to(dev)
+    packed = b200q.pack_w4(qw.to(dev))
+    res = torch.randn(M, N, generator=g).to(dev)
+    gate = torch.randn(N, generator=g).to(dev)
+    outs = {}
+    for expand in (True, False):
+        b200q.w4_expand = expand
+        try:
+            outs[expand] = (
+                b200q.gemm_w4a8(qa.to(dev), packed, K, da, dw, zp, rs, bias, out_dtype=torch.float32),
+                b200q.gemm_w4a8(qa.to(dev), packed, K, da, dw, zp, rs, bias, epilogue=b200q.EPI_GELU_TANH),
+                b200q.gemm_w4a8(qa.to(dev), packed, K, da, dw, zp, rs, bias, out_dtype=torch.float32,
+                                epilogue=b200q.EPI_GATE_RESIDUAL, residual=res.clone(), gate=gate))
+        finally:
+            b200q.w4_expand = True
+    for a, b in zip(outs[True], outs[False]):
+        assert torch.equal(a, b)
+    acc = O.int_accumulators(qa, qw).double() + zp.cpu().double()[None, :] * rs.cpu().double()[:, None]
+    ref = da.cpu().double()[:, None] * dw.cpu().double()[None, :] * acc + bias.cpu().double()[None, :]
+    rel = float(((outs[True][0].cpu().double() - ref).abs() / (ref.abs() + 1.0)).max())
+    assert rel <= 2e-5, rel

@@ -45,11 +45,8 @@ def run(name, fn, secs=2.5):
 
 
 b200q.attn_bf16_set_fast(-1)
-for md in (0, 1, 2, 3):
-    b200q.attn_bf16_set_mode(md)
-    run(f"b200q online softmax poly {md}/8", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
-b200q.attn_bf16_set_mode(2)
-for pp in (0, 1, 2, 3, 4):
+run("b200q online softmax poly 2/8", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
+for pp in (2, 3, 4):
     b200q.attn_bf16_set_fast(pp)
     run(f"b200q max-free poly {pp}/8", lambda: b200q.attn_bf16(q, k, v, H))
 run("library SDPA (cuDNN)", lambda: M.sdpa(q, k, v, H))

@@ -49,7 +49,7 @@ _SIGNATURES = {
                                 c_int, c_void_p, c_int64, c_void_p, c_void_p]),
     "b200q_gemm_w4a8": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_int, c_void_p, c_int, c_int64, c_int64, c_int64, c_int64,
-                                c_int, c_void_p, c_int64, c_void_p, c_void_p]),
+                                c_int, c_void_p, c_int64, c_void_p, c_void_p, c_void_p]),
     "b200q_gemm_set_cluster": (c_int, [c_int]),
     "b200q_pack_w4": (c_int, [c_void_p, c_int64, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_ln_mod_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_float,
@@ -238,7 +238,18 @@ def calib_update(x, absmax=None, xmin=None, xmax=None):
 # ---------------------------------------------------------------------------------------------
 # (b) quantized linear
 # ---------------------------------------------------------------------------------------------
-def _gemm(fn_name, qa, qw, N, K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype, epilogue, residual, gate, out):
+_w4_expand_ws = {}          # device -> reusable scratch for gemm_w4a8's once-per-call weight expansion (stream-ordered reuse)
+
+
+def _w4_scratch(device, nbytes):
+    ws = _w4_expand_ws.get(device)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+        _w4_expand_ws[device] = ws
+    return ws
+
+
+def _gemm(fn_name, qa, qw, N, K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype, epilogue, residual, gate, out, extra=()):
     _cuda(qa, "qa"); _cuda(qw, "qw")
     M = qa.shape[0]
     if out is None:
@@ -250,7 +261,7 @@ def _gemm(fn_name, qa, qw, N, K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dty
     fn = getattr(load(), fn_name)
     rc = fn(_ptr(qa), _ld(qa), _ptr(qw), _ld(qw), _ptr(delta_a), _ptr(delta_w), _ptr(zp_w), _ptr(rowsum_a),
             _ptr(bias), bias_dt, _ptr(out), _DTYPE[out.dtype], _ld(out), M, N, K, int(epilogue),
-            _ptr(residual), _ld(residual) if residual is not None else 0, _ptr(gate), _stream())
+            _ptr(residual), _ld(residual) if residual is not None else 0, _ptr(gate), *extra, _stream())
     _check(rc, fn_name)
     return out
 
@@ -264,6 +275,9 @@ def gemm_w8a8(qa, qw, delta_a=None, delta_w=None, zp_w=None, rowsum_a=None, bias
         raise B200QError(f"gemm_w8a8: K mismatch {qa.shape} vs {qw.shape}")
     return _gemm("b200q_gemm_w8a8", qa, qw, qw.shape[0], K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype,
                  epilogue, residual, gate, out)
+
+
+w4_expand = True            # gemm_w4a8: expand the packed weights once per call when M >= 1024 (False = in-kernel converter)
 
 
 def pack_w4(codes):
@@ -285,8 +299,11 @@ def gemm_w4a8(qa, qw4, K, delta_a=None, delta_w=None, zp_w=None, rowsum_a=None, 
     the unsigned-nibble bias is folded through the zero-point term)."""
     if out_dtype == torch.int32:
         raise B200QError("gemm_w4a8: raw accumulators carry the +8 nibble bias; request a dequantised output")
+    ws = None
+    if w4_expand and qa.shape[0] >= 1024:                     # many-token GEMM: expand the weights once per call (b200q.h)
+        ws = _w4_scratch(qa.device, qw4.shape[0] * ((K + 31) // 32) * 32)
     return _gemm("b200q_gemm_w4a8", qa, qw4, qw4.shape[0], K, delta_a, delta_w, zp_w, rowsum_a, bias, out_dtype,
-                 epilogue, residual, gate, out)
+                 epilogue, residual, gate, out, extra=(_ptr(ws),))
 
 
 # ---------------------------------------------------------------------------------------------

@@ -144,19 +144,26 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   return r;
 }
 
-// Bounded mbarrier wait without the diagnostic printf of ptx::mbar_wait (code size: the softmax loop has to stay inside
-// the instruction cache); a protocol bug still surfaces as a launch failure.
+// Bounded mbarrier wait, written as one PTX loop: a waiting warp is woken by every barrier event of the CTA (ncu: 4-13
+// wake-ups per wait), so the instructions per failed attempt are what a wait costs - try_wait, one add, one compare, one
+// branch.  A protocol bug still surfaces as a launch failure: after 2^20 failed attempts (each suspends up to 20 us when
+// nothing happens at all) the warp traps.
 __device__ __forceinline__ void bar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t spins = 0;
-  long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 255u) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) __trap();
-    }
-  }
+  asm volatile(
+      "{\n"
+      ".reg .pred P1, P2;\n"
+      ".reg .u32 cnt;\n"
+      "mov.u32 cnt, 0;\n"
+      "B200Q_WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+      "@P1 bra.uni B200Q_DONE_%=;\n"
+      "add.u32 cnt, cnt, 1;\n"
+      "setp.lt.u32 P2, cnt, 0x100000;\n"
+      "@P2 bra.uni B200Q_WAIT_%=;\n"
+      "trap;\n"
+      "B200Q_DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
 }
 
 // Critical-path waits (S ready / P ready): selectable polling flavour, b200q_attn_bf16_set_mode bits 64 / 128.

@@ -81,12 +81,20 @@ __device__ __forceinline__ float load_bias(const void* bias, int dtype, int n) {
   return __half2float(reinterpret_cast<const __half*>(bias)[n]);
 }
 
-__device__ __forceinline__ float gelu_tanh(float x) {
-  // torch GELU(approximate='tanh') (wan/modules/model.py:287); tanh on the MUFU (tanh.approx.f32)
-  const float u = 0.7978845608028654f * fmaf(0.044715f * x * x, x, x);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
-  return 0.5f * x * (1.f + t);
+// torch GELU(approximate='tanh') (wan/modules/model.py:287) on two values, packed fp32x2 math + tanh on the MUFU:
+//   0.5 x (1 + tanh(c (x + 0.044715 x^3))) = h + h tanh(x (c + 0.044715 c x^2)),  h = x / 2, c = sqrt(2 / pi)
+// five FMA-pipe issue slots per PAIR (FMUL2, FFMA2, FMUL2, FMUL2, FFMA2) and one MUFU.TANH per value: the epilogue of the
+// ffn.0 GEMM was issue-bound with the scalar form (ncu: 49 % issue, 64 % tensor pipe).
+__device__ __forceinline__ uint64_t gelu_tanh2(uint64_t x2) {
+  const uint64_t s2 = mul_f32x2(x2, x2);
+  const uint64_t w2 = fma_f32x2(s2, pack_f32x2(0.035677408136300125f, 0.035677408136300125f),
+                                pack_f32x2(0.7978845608028654f, 0.7978845608028654f));
+  float u0, u1, t0, t1;
+  unpack_f32x2(mul_f32x2(w2, x2), u0, u1);
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t0) : "f"(u0));
+  asm("tanh.approx.f32 %0, %1;" : "=f"(t1) : "f"(u1));
+  const uint64_t h2 = mul_f32x2(x2, pack_f32x2(0.5f, 0.5f));
+  return fma_f32x2(h2, pack_f32x2(t0, t1), h2);
 }
 
 template <typename OutT> struct OutPack;    // 16-byte chunk = ELEMS outputs
@@ -358,6 +366,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       const int row = m0 + quarter * 32 + lane;
       const float da = (!RAW && row < p.M) ? p.delta_a[row] : 0.f;
       const int rs = (!RAW && p.rowsum_a && row < p.M) ? p.rowsum_a[row] : 0;   // only read when a zero point is in play
+      const uint64_t da2 = pack_f32x2(da, da);
 
       mbar_wait(&tmem_full_bar[as], aphase);
       tcgen05_fence_after();
@@ -402,11 +411,13 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
                 const float dwv[4] = {dw4.x, dw4.y, dw4.z, dw4.w}, bv[4] = {b4.x, b4.y, b4.z, b4.w};
                 const int zv[4] = {z4.x, z4.y, z4.z, z4.w};
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                  const int acc = (int)v[c * ELEMS + 4 * g4 + e] + zv[e] * rs;
-                  float t = fmaf((float)acc, da * dwv[e], bv[e]);
-                  if (EPI == B200Q_EPI_GELU_TANH) t = gelu_tanh(t);
-                  y[4 * g4 + e] = t;
+                for (int e = 0; e < 4; e += 2) {                 // two outputs per packed fp32x2 operation
+                  const int acc0 = (int)v[c * ELEMS + 4 * g4 + e] + zv[e] * rs;
+                  const int acc1 = (int)v[c * ELEMS + 4 * g4 + e + 1] + zv[e + 1] * rs;
+                  const uint64_t sc2 = mul_f32x2(pack_f32x2(dwv[e], dwv[e + 1]), da2);
+                  uint64_t t2 = fma_f32x2(pack_f32x2((float)acc0, (float)acc1), sc2, pack_f32x2(bv[e], bv[e + 1]));
+                  if (EPI == B200Q_EPI_GELU_TANH) t2 = gelu_tanh2(t2);
+                  unpack_f32x2(t2, y[4 * g4 + e], y[4 * g4 + e + 1]);
                 }
               }
               if (GATE) {                                    // residual (fp32 x4) sits where the output goes
@@ -548,7 +559,7 @@ template <bool W4>
 int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, const float* delta_a,
                    const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
                    void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
-                   const float* residual, int64_t ldr, const float* gate, cudaStream_t st) {
+                   const float* residual, int64_t ldr, const float* gate, cudaStream_t st, int zp_offset = 0) {
   B200Q_REQUIRE(M >= 0 && N >= 0 && K >= 0, B200Q_ERR_BAD_ARG, "gemm: negative shape");
   if (M == 0 || N == 0) return B200Q_OK;
   B200Q_REQUIRE(K > 0, B200Q_ERR_BAD_ARG, "gemm: K must be > 0");
@@ -556,7 +567,7 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
   B200Q_REQUIRE(qa && qw && out, B200Q_ERR_BAD_ARG, "gemm: null operand pointer");
   const int64_t kw_bytes = W4 ? ((K + 7) / 8) * 4 : K;      // bytes of one weight row
   B200Q_REQUIRE(lda >= K && ldw >= kw_bytes && ldo >= N, B200Q_ERR_BAD_ARG, "gemm: leading dimension too small");
-  B200Q_REQUIRE(!W4 || rowsum_a != nullptr || out_dtype == B200Q_I32, B200Q_ERR_BAD_ARG,
+  B200Q_REQUIRE(!(W4 || zp_offset != 0) || rowsum_a != nullptr || out_dtype == B200Q_I32, B200Q_ERR_BAD_ARG,
                 "gemm_w4a8: rowsum_a is required (the unsigned-nibble bias is folded through the zero-point term)");
   B200Q_REQUIRE(lda % 16 == 0 && ldw % 16 == 0 && aligned(qa, 16) && aligned(qw, 16), B200Q_ERR_BAD_ARG,
                 "gemm: qa/qw must be 16-byte aligned with lda, ldw (bytes) multiples of 16 (TMA global-stride rule)");
@@ -595,7 +606,7 @@ int gemm_i8_common(const int8_t* qa, int64_t lda, const void* qw, int64_t ldw, c
   p.M = (int)M; p.N = (int)N; p.K = (int)K;
   p.delta_a = delta_a; p.delta_w = delta_w; p.zp_w = zp_w; p.rowsum_a = rowsum_a;
   p.bias = bias; p.bias_dtype = bias_dtype; p.gate = gate; p.epilogue = epilogue;
-  p.zp_offset = W4 ? -8 : 0;
+  p.zp_offset = W4 ? -8 : zp_offset;
 
   if (raw) return launch_gemm<int32_t, B200Q_EPI_NONE, W4>(mp, p, st);
   if (epilogue == B200Q_EPI_GATE_RESIDUAL) {
@@ -643,5 +654,14 @@ int gemm_w4a8_impl(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ld
                    const float* residual, int64_t ldr, const float* gate, cudaStream_t st) {
   return gemm_i8_common<true>(qa, lda, qw4, ldw4, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo,
                               M, N, K, epilogue, residual, ldr, gate, st);
+}
+// W4A8 through an expanded copy of the weights: `qw_u8` holds the unsigned nibbles (code + 8) as bytes, so this is the
+// W8A8 kernel with the nibble bias folded through the zero-point term (zp_eff = zp_w - 8), bit-identical accumulators.
+int gemm_w4a8_expanded_impl(const int8_t* qa, int64_t lda, const int8_t* qw_u8, int64_t ldu, const float* delta_a,
+                            const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                            void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
+                            const float* residual, int64_t ldr, const float* gate, cudaStream_t st) {
+  return gemm_i8_common<false>(qa, lda, qw_u8, ldu, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo,
+                               M, N, K, epilogue, residual, ldr, gate, st, -8);
 }
 }  // namespace b200q

@@ -32,6 +32,23 @@ __global__ void __launch_bounds__(256) pack_w4_kernel(const int8_t* __restrict__
   }
 }
 
+// Expansion of a packed weight matrix to one byte per code (the unsigned nibble, code + 8): thread = one 16-byte packed
+// chunk = 32 codes -> two 16-byte stores.  HBM-bound and tiny next to the GEMM it feeds: 8960 x 1536 is 6.9 MB in,
+// 13.8 MB out.
+__global__ void __launch_bounds__(256) unpack_w4_kernel(const uint8_t* __restrict__ packed, int64_t ldp, int64_t N, int64_t chunks,
+                                                         int8_t* __restrict__ out, int64_t ldu) {
+  const int64_t total = N * chunks;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t n = i / chunks, c = i - n * chunks;
+    const uint4 w = *reinterpret_cast<const uint4*>(packed + n * ldp + c * 16);
+    uint4 o0, o1;
+    o0.x = w.x & 0x0F0F0F0Fu; o0.y = (w.x >> 4) & 0x0F0F0F0Fu; o0.z = w.y & 0x0F0F0F0Fu; o0.w = (w.y >> 4) & 0x0F0F0F0Fu;
+    o1.x = w.z & 0x0F0F0F0Fu; o1.y = (w.z >> 4) & 0x0F0F0F0Fu; o1.z = w.w & 0x0F0F0F0Fu; o1.w = (w.w >> 4) & 0x0F0F0F0Fu;
+    uint4* dst = reinterpret_cast<uint4*>(out + n * ldu + c * 32);
+    dst[0] = o0; dst[1] = o1;
+  }
+}
+
 }  // namespace b200q
 
 using namespace b200q;
@@ -58,14 +75,34 @@ int gemm_w4a8_impl(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ld
                    const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
                    void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
                    const float* residual, int64_t ldr, const float* gate, cudaStream_t st);
+int gemm_w4a8_expanded_impl(const int8_t* qa, int64_t lda, const int8_t* qw_u8, int64_t ldu, const float* delta_a,
+                            const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias, int bias_dtype,
+                            void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K, int epilogue,
+                            const float* residual, int64_t ldr, const float* gate, cudaStream_t st);
 }
 
 extern "C" int b200q_gemm_w4a8(const int8_t* qa, int64_t lda, const uint8_t* qw4, int64_t ldw4, const float* delta_a,
                                const float* delta_w, const float* zp_w, const int32_t* rowsum_a, const void* bias,
                                int bias_dtype, void* out, int out_dtype, int64_t ldo, int64_t M, int64_t N, int64_t K,
-                               int epilogue, const float* residual, int64_t ldr, const float* gate,
+                               int epilogue, const float* residual, int64_t ldr, const float* gate, void* expand_ws,
                                b200q_stream_t stream) {
   clear_error();
+  // Many-token GEMMs (the DiT: M = 32,760 ... 75,600): every one of the M/128 row tiles would expand the same weight tile
+  // again in shared memory.  Expanding the matrix ONCE per call into caller scratch costs microseconds (N*K bytes written)
+  // and lets the product run on the W8A8 kernel at its full rate; small M keeps the in-kernel converter.
+  if (expand_ws != nullptr && M >= 1024 && qw4 != nullptr && N > 0 && K > 0) {
+    const int64_t chunks = (K + 31) / 32, ldu = chunks * 32;
+    B200Q_REQUIRE(aligned(expand_ws, 16) && aligned(qw4, 16) && ldw4 % 16 == 0 && ldw4 >= chunks * 16, B200Q_ERR_BAD_ARG,
+                  "gemm_w4a8: expand_ws / qw4 must be 16-byte aligned and ldw4 a multiple of 16 covering ceil(K/32)*16 bytes");
+    const int64_t total = N * chunks;
+    int64_t blocks = (total + 255) / 256;
+    const int64_t cap = (int64_t)sm_count() * 16;
+    if (blocks > cap) blocks = cap;
+    unpack_w4_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(qw4, ldw4, N, chunks, (int8_t*)expand_ws, ldu);
+    B200Q_CHECK_LAUNCH();
+    return gemm_w4a8_expanded_impl(qa, lda, (const int8_t*)expand_ws, ldu, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out,
+                                   out_dtype, ldo, M, N, K, epilogue, residual, ldr, gate, (cudaStream_t)stream);
+  }
   return gemm_w4a8_impl(qa, lda, qw4, ldw4, delta_a, delta_w, zp_w, rowsum_a, bias, bias_dtype, out, out_dtype, ldo, M,
                         N, K, epilogue, residual, ldr, gate, (cudaStream_t)stream);
 }
