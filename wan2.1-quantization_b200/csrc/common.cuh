@@ -251,7 +251,7 @@ template <> struct Vec16<__half> {
 // IEEE fp32 division followed by round-half-even.  With r = RN(1/d) hoisted per row, two
 // Markstein correction steps (exact fma remainders) return RN(x/d) bit-for-bit; this is what
 // div.rn.f32 does internally, minus the per-element reciprocal.  Verified against true
-// division on 2.56e9 random and near-tie cases (tests/test_division_trick.py, oracle/c/).
+// division on 2.56e9 random and near-tie cases (oracle/c/quant_oracle.c:div_hoisted_check, run by tests/test_oracle_golden.py).
 __device__ __forceinline__ float div_rn_hoisted(float x, float d, float r) {
   float q = x * r;
   float e = fmaf(-q, d, x);
