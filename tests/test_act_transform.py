@@ -146,3 +146,34 @@ def test_variant_layer_fused_vs_reference_formula_gpu(dev, kind, n):
     rel = float((y - ref).abs().max() / ref.abs().max())
     cos = float((y.double().flatten() @ ref.double().flatten()) / (y.double().norm() * ref.double().norm()))
     assert cos >= 0.99999 and rel <= 5e-3, (cos, rel)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n,dtype", [(1536, torch.float32), (1536, torch.bfloat16), (1024, torch.float16)])
+def test_had_quant_warp_kernel_vs_tile_kernel_gpu(dev, n, dtype):
+    """n = K*128 rows take the register-resident warp-per-row kernel (csrc/hadamard.cu); the shared-memory tile kernel stays
+    selectable: same function, fp32 rounding order differs (base block before / after the Walsh-Hadamard stages)."""
+    import b200q
+    from qdiff.base.quant_layer import ActPlan
+    g = torch.Generator().manual_seed(n + 1)
+    rows = 1001
+    x = (torch.randn(rows, n, generator=g) * (torch.rand(rows, 1, generator=g) * 4 + 0.1)).to(dtype).to(dev)
+    sign = torch.randint(0, 2, (n,), generator=g).float() * 2 - 1
+    mask = torch.rand(n, generator=g) * 2 + 0.1
+    plan = ActPlan.rotation(n, sign, mask, dev)
+    lib = b200q.load()
+    try:
+        lib.b200q_had_set_mode(0)
+        q0, d0, rs0, y0 = b200q.had_quant_rows(x, plan.colscale, plan.hadK, plan.K, plan.log2w, 8, want_y=True)
+    finally:
+        lib.b200q_had_set_mode(1)
+    q1, d1, rs1, y1 = b200q.had_quant_rows(x, plan.colscale, plan.hadK, plan.K, plan.log2w, 8, want_y=True)
+    scale = float(y0.abs().max())
+    assert float((y0 - y1).abs().max()) <= 4e-6 * scale
+    assert torch.allclose(d0, d1, rtol=1e-5)
+    assert float((q0.float() - q1.float()).abs().max()) <= 1          # a rounding-order difference can move a code by one step
+    assert float((q0 != q1).float().mean()) < 2e-3
+    from oracle import fakequant_oracle as O
+    qo, do, _ = O.quant_rows(y1.cpu(), 8, True, True)
+    assert torch.equal(q1.cpu().float(), qo) and torch.equal(d1.cpu(), do.flatten())
+    assert torch.equal(rs1.cpu(), qo.to(torch.int32).sum(dim=1).to(torch.int32))

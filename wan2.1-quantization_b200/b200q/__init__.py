@@ -72,6 +72,7 @@ _SIGNATURES = {
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
     "b200q_had_quant_rows": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_void_p, c_int, c_int, c_int,
                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "b200q_had_set_mode": (c_int, [c_int]),
     "b200q_gate_residual": (c_int, [c_void_p, c_int, c_int64, c_void_p, c_void_p, c_int64, c_void_p, c_int64,
                                     c_int64, c_int64, c_void_p]),
 }

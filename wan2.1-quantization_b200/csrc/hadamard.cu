@@ -238,6 +238,146 @@ __global__ void __launch_bounds__(HAD_THREADS, KM <= 12 ? 3 : (KM <= 20 ? 2 : 1)
   }
 }
 
+// ---- register-resident variant: one warp owns one row of n = K * 128 channels ---------------------------------------
+// Lane l holds positions 4l .. 4l+3 of every one of the K segments (4K registers), so
+//   * the order-K base block (same position, all segments) is lane-local: K*K multiply-adds per position from registers,
+//     the +-1 matrix broadcast from shared memory; it runs first - H_K (x) I and I (x) H_128 commute;
+//   * the 128-point Walsh-Hadamard transform of a segment is 2 in-lane stages + 5 shuffle stages;
+//   * abs-max, exact division, packing and the code row sum follow without the row ever leaving the registers:
+//     one HBM read, one HBM write, no shared-memory round trips (the CTA-tile kernel below makes five).
+// ~1,100 warp instructions per row against ~3,000 (ncu) for the shared-memory kernel at n = 1536.
+template <typename T, int K>
+__global__ void __launch_bounds__(128, 3) had_quant_warp_kernel(const HadArgs a) {
+  __shared__ float s_h[K * K];
+  for (int i = threadIdx.x; i < K * K; i += 128) s_h[i] = a.hadK[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 4 + warp;
+  if (row >= a.rows) return;
+  const T* xrow = reinterpret_cast<const T*>(a.x) + row * a.ldx + lane * 4;
+
+  // ---- load (one 16- or 8-byte vector per segment), * colscale ----
+  uint64_t v01[K], v23[K];                          // (position 4l, 4l+1) and (4l+2, 4l+3) of segment s, packed fp32x2
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float f0, f1, f2, f3;
+    if constexpr (sizeof(T) == 4) {
+      const uint4 r = ldg_stream16(xrow + s * 128);
+      f0 = __uint_as_float(r.x); f1 = __uint_as_float(r.y); f2 = __uint_as_float(r.z); f3 = __uint_as_float(r.w);
+    } else {
+      const uint2 r = *reinterpret_cast<const uint2*>(xrow + s * 128);
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        f0 = __uint_as_float(r.x << 16); f1 = __uint_as_float(r.x & 0xffff0000u);
+        f2 = __uint_as_float(r.y << 16); f3 = __uint_as_float(r.y & 0xffff0000u);
+      } else {
+        const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&r.x)), b2 = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+        f0 = a2.x; f1 = a2.y; f2 = b2.x; f3 = b2.y;
+      }
+    }
+    v01[s] = pack_f32x2(f0, f1); v23[s] = pack_f32x2(f2, f3);
+    if (a.colscale != nullptr) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(a.colscale + s * 128 + lane * 4));
+      v01[s] = mul_f32x2(v01[s], pack_f32x2(c.x, c.y));
+      v23[s] = mul_f32x2(v23[s], pack_f32x2(c.z, c.w));
+    }
+  }
+
+  // ---- order-K base block across the segments, one position pair at a time (keeps 6K live registers, not 8K) ----
+  {
+    uint64_t o[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      uint64_t acc = 0;                              // (0.f, 0.f)
+#pragma unroll
+      for (int j = 0; j < K; ++j) { const float h = s_h[i * K + j]; acc = fma_f32x2(pack_f32x2(h, h), v01[j], acc); }
+      o[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) v01[i] = o[i];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      uint64_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) { const float h = s_h[i * K + j]; acc = fma_f32x2(pack_f32x2(h, h), v23[j], acc); }
+      o[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) v23[i] = o[i];
+  }
+
+  // ---- 128-point FWHT of every segment: stages over the 4 in-lane positions, then over the 32 lanes ----
+  const uint64_t pm = pack_f32x2(1.f, -1.f);
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float a0, a1, a2, a3;
+    unpack_f32x2(v01[s], a0, a1); unpack_f32x2(v23[s], a2, a3);
+    // stage h = 1: (a0, a1) -> (a0 + a1, a0 - a1); stage h = 2: pairs (0,2), (1,3)
+    const uint64_t p = fma_f32x2(pack_f32x2(a1, a1), pm, pack_f32x2(a0, a0));      // (a0 + a1, a0 - a1)
+    const uint64_t q = fma_f32x2(pack_f32x2(a3, a3), pm, pack_f32x2(a2, a2));      // (a2 + a3, a2 - a3)
+    v01[s] = add_f32x2(p, q);
+    v23[s] = fma_f32x2(q, pack_f32x2(-1.f, -1.f), p);
+  }
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    const float sg = (lane & ofs) ? -1.f : 1.f;     // upper half of the butterfly: other - v, lower: v + other
+    const uint64_t sg2 = pack_f32x2(sg, sg);
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      uint32_t lo, hi;
+      unpack_u32x2(v01[s], lo, hi);
+      const uint64_t o01 = pack_u32x2(__shfl_xor_sync(0xffffffffu, lo, ofs), __shfl_xor_sync(0xffffffffu, hi, ofs));
+      v01[s] = fma_f32x2(v01[s], sg2, o01);
+      unpack_u32x2(v23[s], lo, hi);
+      const uint64_t o23 = pack_u32x2(__shfl_xor_sync(0xffffffffu, lo, ofs), __shfl_xor_sync(0xffffffffu, hi, ofs));
+      v23[s] = fma_f32x2(v23[s], sg2, o23);
+    }
+  }
+
+  // ---- per-token abs-max -> delta ----
+  float m = 0.f;
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float b0, b1, b2, b3;
+    unpack_f32x2(v01[s], b0, b1); unpack_f32x2(v23[s], b2, b3);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(b0), fabsf(b1)), fmaxf(fabsf(b2), fabsf(b3))));
+  }
+  m = warp_max(m);
+  float delta = __fdiv_rn(m, a.n_levels);
+  if (delta < 1.0e-6f) delta = 1.0e-6f;                                  // base_quantizer.py:122-128
+  const float rc = __frcp_rn(delta);
+  const uint64_t r2 = pack_f32x2(rc, rc), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+
+  // ---- quantize, pack 4 codes per lane and segment, store ----
+  int sum = 0;
+  int8_t* qrow = a.q + row * a.ldq + lane * 4;
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    uint32_t c0, c1, c2, c3;
+    unpack_u32x2(div_rn_hoisted_rne2(v01[s], nd2, r2, magic2), c0, c1);
+    unpack_u32x2(div_rn_hoisted_rne2(v23[s], nd2, r2, magic2), c2, c3);
+    const uint32_t packed = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+    sum = __dp4a((int)packed, 0x01010101, sum);
+    stg_stream4(qrow + s * 128, packed);
+    if (a.y_out != nullptr) {
+      float b0, b1, b2, b3;
+      unpack_f32x2(v01[s], b0, b1); unpack_f32x2(v23[s], b2, b3);
+      *reinterpret_cast<float4*>(a.y_out + row * a.ldy + s * 128 + lane * 4) = make_float4(b0, b1, b2, b3);
+    }
+  }
+  if (a.rowsum != nullptr) {
+    sum = warp_sum(sum);
+    if (lane == 0) a.rowsum[row] = sum;
+  }
+  if (lane == 0) a.delta[row] = delta;
+}
+
+template <typename T, int K>
+static int launch_had_warp(const HadArgs& a, cudaStream_t st) {
+  had_quant_warp_kernel<T, K><<<(unsigned)((a.rows + 3) / 4), 128, 0, st>>>(a);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
 template <typename T, int KM>
 static int launch_had_km(const HadArgs& a0, cudaStream_t st) {
   HadArgs a = a0;
@@ -261,8 +401,15 @@ static int launch_had_km(const HadArgs& a0, cudaStream_t st) {
   return B200Q_OK;
 }
 
+static int g_had_warp = 1;          // 0: always the shared-memory tile kernel (tests compare the two)
+
 template <typename T>
 static int launch_had(const HadArgs& a, cudaStream_t st) {
+  const bool vec_ok = aligned(a.x, 16) && (a.ldx * sizeof(T)) % 16 == 0 && a.ldq % 4 == 0;
+  if (g_had_warp && a.log2w == 7 && vec_ok) {       // n = K * 128: the register-resident warp-per-row kernel
+    if (a.K == 8) return launch_had_warp<T, 8>(a, st);
+    if (a.K == 12) return launch_had_warp<T, 12>(a, st);   // 1536 = Wan-1.3B hidden
+  }
   if (a.K <= 12) return launch_had_km<T, 12>(a, st);
   if (a.K <= 20) return launch_had_km<T, 20>(a, st);
   return launch_had_km<T, HAD_KMAX>(a, st);
@@ -271,6 +418,11 @@ static int launch_had(const HadArgs& a, cudaStream_t st) {
 }  // namespace b200q
 
 using namespace b200q;
+
+extern "C" int b200q_had_set_mode(int warp_kernel) {
+  g_had_warp = warp_kernel != 0;
+  return B200Q_OK;
+}
 
 extern "C" int b200q_had_quant_rows(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
                                     const float* colscale, const float* hadK, int K, int log2_width, int n_bits,
