@@ -591,9 +591,17 @@ def run_b200(args):
             own = attn != "library"
             kern = {"b200q": "attn_bf16_kernel (tcgen05.mma.kind::f16, TMA, TMEM; this repo)", "int8": "attn_i8_kernel (tcgen05.mma.kind::i8; this repo)",
                     "library": "torch SDPA (cuDNN flash attention; library, not this repo's code)"}[attn]
+            # DRAM bytes per launch from the committed ncu --set full capture of the same kernel at the 1.3B self-attention
+            # shape (profiles/traffic.json); other shapes have no capture -> null
+            tkey = {"b200q": "attn_bf16_H12_L32760", "int8": "attn_i8_H12_L32760"}.get(attn)
+            traffic = traffic_db.get(tkey) if (tkey and dom_a == "32760x32760x1536") else None
             return {"bound": "tensor", "kernel": f"{kern} Lq,Lk,D={dom_a}", "own_kernel": own, "achieved": ach, "peak": bf16_sus,
-                    "unit": "TFLOP/s", "frac": ach / bf16_sus, "traffic": traffic_db.get("attn", {}).get(dom_a),
-                    "traffic_source": traffic_db.get("source"), "algorithmic_ops_per_launch": o_ / n_, "avg_launch_ms": t_ / n_,
+                    "unit": "TFLOP/s", "frac": ach / bf16_sus, "traffic": traffic,
+                    "traffic_source": traffic_db.get("source") if traffic else None,
+                    "algorithmic_ops_per_launch": o_ / n_, "avg_launch_ms": t_ / n_,
+                    "algorithmic_hbm_bytes_per_launch": 4 * 2 * int(dom_a.split("x")[0]) * int(dom_a.split("x")[2]) if "x" in dom_a else None,
+                    "softmax": ("per-head on the device: max-free softmax for heads whose Cauchy-Schwarz score bound is <= 80 "
+                                "(all heads of this synthetic, unit-RMS workload), online softmax otherwise") if attn == "b200q" else None,
                     "peak_source": bf16_src + " (bf16 dense; flop-equivalents 4*Lq*Lk*D for the int8 kernel)",
                     "frac_of_nominal_2250": ach / 2250.0}
         rl_g, rl_a = gemm_roofline(), attn_roofline()

@@ -242,7 +242,7 @@ B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, 
  *   q bf16 [Lq, H*128] (ldq), k, v bf16 [Lk, H*128] (ldk, ldv): row pitches in elements, multiples of 8, 16-byte aligned
  *   bases - column slices of a fused q|k|v GEMM output are fine.  out bf16 [Lq, H*128] (ldo).
  *   lse_out (optional, fp32 [H, Lq]): log2(sum_j 2^(x_ij)), x = q.k^T * sm_scale * log2(e) (n_splits == 1 only).
- *   n_splits > 1: every (head, 256-query) work item is split along the keys into n_splits items (one persistent CTA per
+ *   n_splits > 1: every (head, 512-query) work item is split along the keys into n_splits items (one persistent CTA per
  *   SM walks the items, so more and shorter items fill the last wave; b200q_attn_bf16_splits proposes the count); the
  *   partial outputs go to part_ws (bf16 [n_splits, Lq, H*128]) with their log-sum-exp in lse_ws (fp32 [n_splits, H, Lq]),
  *   both caller-owned scratch, and a second launch merges them with the weights 2^(lse_s - lse).
@@ -266,6 +266,9 @@ B200Q_API int b200q_attn_bf16_set_mode(int mode);
 /* Max-free kernel of b200q_attn_bf16 (bounded heads): polynomial pairs of every 8 (0..5, default 3 - the fastest under the
  * power cap: 5.48 ms at H=12, L=32760 sustained, against 6.31 ms for the online softmax); -1 disables the max-free kernel (every head takes the online softmax even when qk_norm_ws is given). */
 B200Q_API int b200q_attn_bf16_set_fast(int poly_pairs);
+/* CTAs per work item of b200q_attn_bf16: 2 (default) = CTA pairs, 512 queries per item, tcgen05.mma.cta_group::2 with each
+ * CTA staging half of every K and V tile; 1 = single CTAs, 256 queries per item.  Same function either way. */
+B200Q_API int b200q_attn_bf16_set_cluster(int ctas);
 
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the

@@ -67,6 +67,7 @@ _SIGNATURES = {
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
                                 c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200q_attn_bf16_set_fast": (c_int, [c_int]),
+    "b200q_attn_bf16_set_cluster": (c_int, [c_int]),
     "b200q_attn_bf16_splits": (c_int, [c_int64, c_int64, c_int]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
@@ -449,6 +450,12 @@ def attn_bf16_set_fast(poly_pairs):
     """polynomial pairs of every 8 in the max-free kernel (2..5); -1 = online softmax for every head"""
     if load().b200q_attn_bf16_set_fast(int(poly_pairs)) != 0:
         raise B200QError("b200q_attn_bf16_set_fast: bad value")
+
+
+def attn_bf16_set_cluster(ctas):
+    """1 = single-CTA work items, 2 = CTA pairs with tcgen05.mma.cta_group::2 (default)."""
+    if load().b200q_attn_bf16_set_cluster(int(ctas)) != 0:
+        raise B200QError("b200q_attn_bf16_set_cluster: 1 or 2")
 
 
 def attn_bf16_set_mode(mode):

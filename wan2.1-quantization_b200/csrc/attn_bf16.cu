@@ -46,15 +46,25 @@ constexpr int KS = 2, VS = 2;
 constexpr int THREADS = 18 * 32;             // 16 softmax warps + TMA producer + MMA issuer
 constexpr float RESCALE_THRESHOLD = 8.0f;   // log2 units
 
-struct Smem {
+// CL = CTAs per cluster.  CL == 2: a CTA pair works on 512 queries of one head with tcgen05.mma.cta_group::2 (M = 256: 128
+// query rows from each CTA); each CTA stages only HALF of every K tile (64 of the 128 keys) and HALF of every V tile (64 of
+// the 128 head_dim columns), which halves the TMA / L2 traffic of K and V and cuts the shared-memory operand reads of a
+// Q.K^T instruction from 8 KB to 6 KB per CTA (at M = N = 128 an SS instruction reads shared memory at the 128 B/clk port
+// limit) and those of P.V from 4 KB to 2 KB.  The ring stages are half as large, so the pair runs four of them.
+template <int CL>
+struct SmemT {
+  static constexpr int ks = CL == 2 ? 4 : KS, vs = CL == 2 ? 4 : VS;
+  static constexpr int ktile = TILE / CL, vtile = TILE / CL;   // bytes per ring stage in this CTA
+  static constexpr int khalf = HALF / CL;                      // one K box: (128 / CL) keys x 64 bf16
   static constexpr int q = 0;                       // 2 tiles
-  static constexpr int k = q + 2 * TILE;            // KS tiles
-  static constexpr int v = k + KS * TILE;           // VS tiles
-  static constexpr int xch = v + VS * TILE;          // half-row statistics exchange: [tile][parity][half][row] fp32
+  static constexpr int k = q + 2 * TILE;            // ks stages
+  static constexpr int v = k + ks * ktile;          // vs stages
+  static constexpr int xch = v + vs * vtile;         // half-row statistics exchange: [tile][parity][half][row] fp32
   static constexpr int bar = xch + 2 * 2 * 2 * 128 * 4;
   static constexpr int total = bar + 256;
 };
-static_assert(Smem::total <= 232448, "dynamic smem budget (227 KB) exceeded");
+using Smem = SmemT<1>;
+static_assert(SmemT<1>::total <= 232448 && SmemT<2>::total <= 232448, "dynamic smem budget (227 KB) exceeded");
 
 struct Params {
   int Lq, Lk, H;
@@ -114,6 +124,32 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, ui
       "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
       "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
       : "memory");
+}
+// cta_group::2 forms: D = 256 x N over both CTAs' TMEM (128 lanes each), A = 128 rows from each CTA (shared memory at the
+// same CTA-relative address, or each CTA's own TMEM columns), B = N/2 rows from each CTA's shared memory
+__device__ __forceinline__ void mma_bf16_ss_2sm(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void mma_bf16_ts_2sm(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], [%1], %2, %3, p;\n}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier given by its shared::cluster address (mapa): the softmax warps of both CTAs of a pair report to the
+// LEADER's barriers, whose MMA warp issues the pair's instructions.  RELAXED on purpose: what the arrival publishes lives in
+// tensor memory and is ordered by tcgen05.wait::st / ::ld + tcgen05.fence::before_thread_sync on this side and
+// tcgen05.fence::after_thread_sync on the waiting side; a release at cluster scope would put MEMBAR.ALL.GPU + ERRBAR in
+// front of every arrival (and an acquire.cluster wait a CCTL.IVALL behind every wait) on the critical S -> P -> P.V chain.
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t* v) {
   asm volatile(
@@ -305,10 +341,12 @@ __device__ __forceinline__ long long tr_clock() { long long c; asm volatile("mov
 #define TR(i)
 #endif
 
-template <int POLY, bool FAST>
+template <int POLY, bool FAST, int CL>
 __global__ void __launch_bounds__(THREADS, 1)
 attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                  const __grid_constant__ CUtensorMap tm_v, const Params p) {
+  using Smem = SmemT<CL>;
+  constexpr int KS = Smem::ks, VS = Smem::vs;
   extern __shared__ __align__(1024) uint8_t smem[];
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
@@ -329,24 +367,29 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nb_all = (p.Lk + BKEY - 1) / BKEY;
-  // item -> (head, key split, query-tile pair); a split covers key blocks [kb0, kb0 + nb)
+  // item -> (head, key split, group of 2 * CL query tiles); a split covers key blocks [kb0, kb0 + nb).  Items are walked by
+  // clusters; CTA `rank` of a pair owns query rows [rank * 256, rank * 256 + 256) of the item's 512.
   const int per_head = p.n_qt * p.n_splits;
+  const int rank = (CL == 2) ? (int)cluster_ctarank() : 0;
+  const int item0 = (int)blockIdx.x / CL, item_step = (int)gridDim.x / CL;
+  constexpr uint16_t kPair = 3;
 
   if (threadIdx.x == 0) {
     mbar_init(q_full, 1); mbar_init(q_empty, 1);
     for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
     for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8);
-      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8);
+    for (int i = 0; i < 2; ++i) {                      // CL == 2: both CTAs' softmax warps report to the leader
+      mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 8 * CL);
+      mbar_init(&o_full[i], 1); mbar_init(&o_free[i], 8 * CL);
     }
     fence_barrier_init();
   }
   constexpr int W_TMA = 16, W_MMA = 17;
   if (warp == W_TMA && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
-  if (warp == W_TMA) tmem_alloc<512>(tmem_slot);
+  if (warp == W_TMA) { if (CL == 2) tmem_alloc_2sm<512>(tmem_slot); else tmem_alloc<512>(tmem_slot); }
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync();                           // the peer's barriers exist before anyone signals them
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -354,38 +397,65 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // ===================== TMA producer =====================
     if (lane == 0) {
       int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ);
+      for (int item = item0; item < p.n_items; item += item_step) {
+        const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ * CL) + rank * (2 * BQ);
         if (head_is_bounded(p, h) != FAST) continue;                      // the other kernel's head
         const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
         bar_wait(q_empty, (it & 1) ^ 1);
         ++it;
-        mbar_expect_tx(q_full, 2 * TILE);
+        if (CL == 2) {
+          // the leader's MMA warp reads both CTAs' operands: every byte of the pair is credited to the LEADER's barrier
+          const uint32_t lead = mapa_u32(q_full, 0);
+          if (rank == 0) mbar_expect_tx(q_full, 4 * TILE);
 #pragma unroll
-        for (int t = 0; t < 2; ++t)
+          for (int t = 0; t < 2; ++t)
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf)
-            tma_load_2d(smem + Smem::q + t * TILE + hf * HALF, &tm_q, q_full, h * HD + hf * 64, q0 + t * BQ);
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_2d_2sm(smem + Smem::q + t * TILE + hf * HALF, &tm_q, lead, h * HD + hf * 64, q0 + t * BQ);
+        } else {
+          mbar_expect_tx(q_full, 2 * TILE);
+#pragma unroll
+          for (int t = 0; t < 2; ++t)
+#pragma unroll
+            for (int hf = 0; hf < 2; ++hf)
+              tma_load_2d(smem + Smem::q + t * TILE + hf * HALF, &tm_q, q_full, h * HD + hf * 64, q0 + t * BQ);
+        }
         for (int j = 0; j < nb; ++j) {
           bar_wait(&k_empty[ks], kph ^ 1);
-          mbar_expect_tx(&k_full[ks], TILE);
-          tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, (kb0 + j) * BKEY);
-          tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, (kb0 + j) * BKEY);
+          if (CL == 2) {
+            // my half of the key block: keys [rank * 64, rank * 64 + 64), all 128 head_dim columns (two 64 x 64 boxes)
+            const uint32_t lead = mapa_u32(&k_full[ks], 0);
+            if (rank == 0) mbar_expect_tx(&k_full[ks], TILE);
+            tma_load_2d_2sm(smem + Smem::k + ks * Smem::ktile, &tm_k, lead, h * HD, (kb0 + j) * BKEY + rank * 64);
+            tma_load_2d_2sm(smem + Smem::k + ks * Smem::ktile + Smem::khalf, &tm_k, lead, h * HD + 64, (kb0 + j) * BKEY + rank * 64);
+          } else {
+            mbar_expect_tx(&k_full[ks], TILE);
+            tma_load_2d(smem + Smem::k + ks * TILE, &tm_k, &k_full[ks], h * HD, (kb0 + j) * BKEY);
+            tma_load_2d(smem + Smem::k + ks * TILE + HALF, &tm_k, &k_full[ks], h * HD + 64, (kb0 + j) * BKEY);
+          }
           if (++ks == KS) { ks = 0; kph ^= 1; }
           bar_wait(&v_empty[vs], vph ^ 1);
-          mbar_expect_tx(&v_full[vs], TILE);
-          tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, (kb0 + j) * BKEY);
-          tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, (kb0 + j) * BKEY);
+          if (CL == 2) {
+            // my half of the value block: all 128 keys, head_dim columns [rank * 64, rank * 64 + 64) (one 128 x 64 box)
+            const uint32_t lead = mapa_u32(&v_full[vs], 0);
+            if (rank == 0) mbar_expect_tx(&v_full[vs], TILE);
+            tma_load_2d_2sm(smem + Smem::v + vs * Smem::vtile, &tm_v, lead, h * HD + rank * 64, (kb0 + j) * BKEY);
+          } else {
+            mbar_expect_tx(&v_full[vs], TILE);
+            tma_load_2d(smem + Smem::v + vs * TILE, &tm_v, &v_full[vs], h * HD, (kb0 + j) * BKEY);
+            tma_load_2d(smem + Smem::v + vs * TILE + HALF, &tm_v, &v_full[vs], h * HD + 64, (kb0 + j) * BKEY);
+          }
           if (++vs == VS) { vs = 0; vph ^= 1; }
         }
       }
     }
   } else if (warp == W_MMA) {
-    // ===================== MMA issuer =====================
+    if (CL == 1 || rank == 0) {
+    // ===================== MMA issuer (CL == 2: the leader CTA issues for the pair) =====================
     // The whole warp walks the schedule (uniform control flow keeps descriptors and addresses in uniform registers); one
     // elected lane issues the tcgen05 instructions.
-    constexpr uint32_t idesc_qk = idesc_bf16(BQ, BKEY, false);
-    constexpr uint32_t idesc_pv = idesc_bf16(BQ, HD, true);
+    constexpr uint32_t idesc_qk = idesc_bf16(BQ * CL, BKEY, false);
+    constexpr uint32_t idesc_pv = idesc_bf16(BQ * CL, HD, true);
     int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
     uint32_t pcnt0 = 0, pcnt1 = 0;                    // P tiles consumed so far per Q tile
     const uint64_t qd0 = make_kmajor_sw128_desc(smem_u32(smem + Smem::q));
@@ -395,17 +465,19 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     // S[t] = Q_t . K(stage)^T : 8 x (M128, N128, K16); k-step kk: head_dim half kk / 4, 32 bytes per step inside the 128 B row
     auto qk = [&](int t, int stage) {
       const uint64_t a0 = t ? qd1 : qd0;
-      const uint64_t b0 = kd + (uint64_t)(stage * (TILE >> 4));
+      const uint64_t b0 = kd + (uint64_t)(stage * (Smem::ktile >> 4));
       const uint32_t d = tmem_base + t * 128;
       if (elect_one()) {
         if (!(p.mode & 16)) {
 #pragma unroll
           for (int kk = 0; kk < HD / 16; ++kk) {
             const uint64_t off = (uint64_t)((kk >> 2) * (HALF >> 4) + (kk & 3) * 2);
-            mma_bf16_ss(d, a0 + off, b0 + off, idesc_qk, kk != 0 ? 1u : 0u);
+            const uint64_t boff = (uint64_t)((kk >> 2) * (Smem::khalf >> 4) + (kk & 3) * 2);
+            if (CL == 2) mma_bf16_ss_2sm(d, a0 + off, b0 + boff, idesc_qk, kk != 0 ? 1u : 0u);
+            else mma_bf16_ss(d, a0 + off, b0 + boff, idesc_qk, kk != 0 ? 1u : 0u);
           }
         }
-        mma_commit(&s_full[t]);
+        if (CL == 2) mma_commit_2sm_mc(&s_full[t], kPair); else mma_commit(&s_full[t]);
       }
       __syncwarp();
     };
@@ -413,26 +485,29 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     auto pv = [&](int t, int stage, bool first) {
       if (t == 0) { bar_wait_crit(&p_full[0], pcnt0 & 1, p.mode); ++pcnt0; } else { bar_wait_crit(&p_full[1], pcnt1 & 1, p.mode); ++pcnt1; }
       tcgen05_fence_after();
-      const uint64_t b0 = vd + (uint64_t)(stage * (TILE >> 4));
+      const uint64_t b0 = vd + (uint64_t)(stage * (Smem::vtile >> 4));
       const uint32_t d = tmem_base + 256 + t * 128;
       const uint32_t pa = tmem_base + t * 128;
       if (elect_one() && !(p.mode & 16)) {
         // P columns: the online-softmax kernel packs the row's 128 keys into S columns 0..63; the max-free kernel leaves
         // each half-row thread's 64 keys in the first 32 of ITS OWN 64 S columns (no cross-thread hazard, no barrier)
 #pragma unroll
-        for (int kk = 0; kk < BKEY / 16; ++kk)
-          mma_bf16_ts(d, pa + (FAST ? (kk >> 2) * 64 + (kk & 3) * 8 : kk * 8), b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv,
-                      (first && kk == 0) ? 0u : 1u);
+        for (int kk = 0; kk < BKEY / 16; ++kk) {
+          const uint32_t a = pa + (FAST ? (kk >> 2) * 64 + (kk & 3) * 8 : kk * 8);
+          if (CL == 2) mma_bf16_ts_2sm(d, a, b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (first && kk == 0) ? 0u : 1u);
+          else mma_bf16_ts(d, a, b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (first && kk == 0) ? 0u : 1u);
+        }
       }
       __syncwarp();
     };
     auto commit = [&](uint64_t* bar) {
-      if (elect_one()) mma_commit(bar);
+      if (elect_one()) { if (CL == 2) mma_commit_2sm_mc(bar, kPair); else mma_commit(bar); }
       __syncwarp();
     };
+    auto wait_o_free = [&](int t, uint32_t parity) { bar_wait(&o_free[t], parity); };
     auto next_k = [&]() { commit(&k_empty[ks]); if (++ks == KS) { ks = 0; kph ^= 1; } };
     auto next_v = [&]() { commit(&v_empty[vs]); if (++vs == VS) { vs = 0; vph ^= 1; } };
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++it) {
+    for (int item = item0; item < p.n_items; item += item_step, ++it) {
       if (head_is_bounded(p, item / per_head) != FAST) { --it; continue; }
       const int nb = min(p.bps, nb_all - ((item % per_head) / p.n_qt) * p.bps);
       TR_DECL;
@@ -442,7 +517,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
       qk(0, ks);
       qk(1, ks);
       next_k();
-      bar_wait(&o_free[0], it & 1);                         // previous item's O0 has been read out
+      wait_o_free(0, it & 1);                               // previous item's O0 has been read out
       bar_wait(&v_full[vs], vph);
       pv(0, vs, true);
       for (int j = 1; j < nb; ++j) {
@@ -451,7 +526,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         TR(1);
         tcgen05_fence_after();
         qk(0, ks);                                           // S0(j): in order behind P0.V(j-1), which read P0 = S0's columns
-        if (j == 1) bar_wait(&o_free[1], it & 1);
+        if (j == 1) wait_o_free(1, it & 1);
         TR(2);
         pv(1, vs, j == 1);                                   // P1.V(j-1)
         TR(3);
@@ -471,10 +546,11 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 #endif
       commit(&o_full[0]);
       commit(q_empty);                                       // last read of the Q tiles was S1(nb-1)
-      if (nb == 1) bar_wait(&o_free[1], it & 1);
+      if (nb == 1) wait_o_free(1, it & 1);
       pv(1, vs, nb == 1);                                    // P1.V(nb-1)
       next_v();
       commit(&o_full[1]);
+    }
     }
   } else {
     // ===================== softmax warps: thread = (query row, half of the key block) =====================
@@ -489,13 +565,18 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
     const float c = p.scale_log2e;
     const uint64_t c2 = pack_f32x2(c, c);
     const int tail = p.Lk - (nb_all - 1) * BKEY;                         // valid keys in the last block (1..128)
+    // where this warp reports "P written" / "O read out": its own CTA's barriers, or (CL == 2) the leader's
+    const uint32_t pf_addr = CL == 2 ? mapa_u32(&p_full[t], 0) : 0u, of_addr = CL == 2 ? mapa_u32(&o_free[t], 0) : 0u;
+    auto arrive_p = [&]() { if (CL == 2) mbar_arrive_cluster(pf_addr); else mbar_arrive(&p_full[t]); };
+    auto arrive_o = [&]() { if (CL == 2) mbar_arrive_cluster(of_addr); else mbar_arrive(&o_free[t]); };
     {                                                                    // O columns start out free
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[t]);
+      if (lane == 0) arrive_o();
     }
-    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x, ++itn) {
-      const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + t * BQ;
+    for (int item = item0; item < p.n_items; item += item_step, ++itn) {
+      const int h = item / per_head, sp = (item % per_head) / p.n_qt;
+      const int q0 = (item % p.n_qt) * (2 * BQ * CL) + rank * (2 * BQ) + t * BQ;
       if (head_is_bounded(p, h) != FAST) { --itn; continue; }
       const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
       const int row = q0 + r;
@@ -548,7 +629,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) arrive_p();
         TR(6);
       }
       for (int j = 0; !FAST && j < nb; ++j) {
@@ -560,7 +641,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (p.mode & 8) {                                                // diagnostic: tensor / TMA pipeline alone
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
+          if (lane == 0) arrive_p();
           continue;
         }
         uint32_t sr[4][16];                                              // my half of the S row
@@ -600,7 +681,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
           if (nm == 12345.f) tmem_st_32x16(t_p, sr[0]);
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&p_full[t]);
+          if (lane == 0) arrive_p();
           continue;
         }
 #pragma unroll
@@ -614,7 +695,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[t]);
+        if (lane == 0) arrive_p();
         TR(6);
       }
 #ifdef B200Q_FA_TRACE
@@ -643,7 +724,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
         if (ch == 3) {                                                   // O is in registers: hand the columns back
           tcgen05_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&o_free[t]);
+          if (lane == 0) arrive_o();
         }
         if (row_ok) {
 #pragma unroll
@@ -662,8 +743,9 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
 
   tcgen05_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync();                           // the peer may still signal this CTA's barriers / read its operands
   tcgen05_fence_after();
-  if (warp == W_TMA) tmem_dealloc<512>(tmem_base);
+  if (warp == W_TMA) { if (CL == 2) tmem_dealloc_2sm<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
 // Per-head maxima of the squared row norms: norms[h] = max_i |q_i,h|^2 (blockIdx.y = h), norms[H + h] = max_j |k_j,h|^2
@@ -745,6 +827,7 @@ using namespace b200q;
 // +32 = softmax warps stop after the TMEM load, row maximum and exchange.
 static int g_fa_mode = 2;
 static int g_fa_fast_poly = 3;      // max-free kernel: polynomial pairs of every 8 (0..5); -1 = never use the max-free kernel
+static int g_fa_cl = 2;             // CTAs per cluster: 2 = CTA pairs with tcgen05.mma.cta_group::2 (default), 1 = single CTAs
 extern "C" int b200q_attn_bf16_set_mode(int mode) {
   if (mode < 0 || mode > 255 || (mode & 4)) return B200Q_ERR_BAD_ARG;
   g_fa_mode = mode;
@@ -755,6 +838,11 @@ extern "C" int b200q_attn_bf16_set_fast(int poly_pairs) {
   g_fa_fast_poly = poly_pairs;
   return B200Q_OK;
 }
+extern "C" int b200q_attn_bf16_set_cluster(int ctas) {
+  if (ctas != 1 && ctas != 2) return B200Q_ERR_BAD_ARG;
+  g_fa_cl = ctas;
+  return B200Q_OK;
+}
 
 // How many key splits b200q_attn_bf16 should use for this shape (1 = none): (head, query-tile pair) items are walked by one
 // persistent CTA per SM, so a grid that is not a multiple of the SM count leaves a partial last wave; splitting the keys
@@ -762,8 +850,9 @@ extern "C" int b200q_attn_bf16_set_fast(int poly_pairs) {
 extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
   using namespace fa;
   if (Lq <= 0 || Lk <= 0 || num_heads <= 0) return 1;
-  const long long items = ((Lq + 2 * BQ - 1) / (2 * BQ)) * num_heads;
-  const int nb = (int)((Lk + BKEY - 1) / BKEY), sms = sm_count();
+  const int cl = g_fa_cl;                                             // items are walked by clusters of cl CTAs
+  const long long items = ((Lq + 2 * BQ * cl - 1) / (2 * BQ * cl)) * num_heads;
+  const int nb = (int)((Lk + BKEY - 1) / BKEY), sms = sm_count() / cl;
   int best = 1;
   double best_cost = 0;
   for (int S = 1; S <= 4; ++S) {
@@ -773,6 +862,43 @@ extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
     if (S == 1 || cost < best_cost * 0.97) { if (S == 1 || cost < best_cost) { best = s_eff; best_cost = cost; } }
   }
   return best;
+}
+
+// One launch of the persistent kernel: one CTA per SM, whole clusters only.
+template <int POLY, bool FAST, int CL>
+static int launch_fa(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::Params& p, cudaStream_t st) {
+  using namespace fa;
+  static bool configured = false;
+  if (!configured) {
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<POLY, FAST, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemT<CL>::total));
+    configured = true;
+  }
+  const int cap = (sm_count() / CL) * CL;
+  const int grid = p.n_items * CL < cap ? p.n_items * CL : cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemT<CL>::total; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B200Q_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_bf16_kernel<POLY, FAST, CL>, tq, tk, tv, p));
+  return B200Q_OK;
+}
+template <bool FAST, int CL>
+static int launch_fa_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::Params& p, cudaStream_t st) {
+  switch (poly) {
+    case 0: return launch_fa<0, FAST, CL>(tq, tk, tv, p, st);
+    case 1: return launch_fa<1, FAST, CL>(tq, tk, tv, p, st);
+    case 2: return launch_fa<2, FAST, CL>(tq, tk, tv, p, st);
+    case 4: return launch_fa<FAST ? 4 : 3, FAST, CL>(tq, tk, tv, p, st);      // 4 and 5 exist for the max-free kernel only
+    case 5: return launch_fa<FAST ? 5 : 3, FAST, CL>(tq, tk, tv, p, st);
+    default: return launch_fa<3, FAST, CL>(tq, tk, tv, p, st);
+  }
+}
+static int launch_fa_any(bool fast, int poly, int cl, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+                         const fa::Params& p, cudaStream_t st) {
+  if (cl == 2) return fast ? launch_fa_poly<true, 2>(poly, tq, tk, tv, p, st) : launch_fa_poly<false, 2>(poly, tq, tk, tv, p, st);
+  return fast ? launch_fa_poly<true, 1>(poly, tq, tk, tv, p, st) : launch_fa_poly<false, 1>(poly, tq, tk, tv, p, st);
 }
 
 extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
@@ -790,16 +916,17 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   B200Q_REQUIRE(ldq % 8 == 0 && ldk % 8 == 0 && ldv % 8 == 0 && ldo % 8 == 0 && aligned(q, 16) && aligned(k, 16) && aligned(v, 16) &&
                     aligned(out, 16),
                 B200Q_ERR_BAD_ARG, "attn_bf16: q/k/v/out must be 16-byte aligned bf16 with row pitches that are multiples of 8");
+  const int cl = g_fa_cl;
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_tmap_2d(&tq, q, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lq, D, ldq, BQ, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
-  if ((rc = make_tmap_2d(&tk, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldk, BKEY, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+  if ((rc = make_tmap_2d(&tk, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldk, BKEY / cl, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   if ((rc = make_tmap_2d(&tv, v, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldv, BKEY, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
   Params p{};
   p.Lq = (int)Lq; p.Lk = (int)Lk; p.H = num_heads;
   p.out = (__nv_bfloat16*)out; p.ldo = ldo;
   p.scale_log2e = sm_scale * 1.4426950408889634f;
-  p.n_qt = (int)((Lq + 2 * BQ - 1) / (2 * BQ));
+  p.n_qt = (int)((Lq + 2 * BQ * cl - 1) / (2 * BQ * cl));
   const int nb_all = (int)((Lk + BKEY - 1) / BKEY);
   if (n_splits < 1) n_splits = 1;
   if (n_splits > 8) n_splits = 8;
@@ -816,21 +943,6 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   p.n_items = p.n_qt * num_heads * p.n_splits;
   p.mode = g_fa_mode;
   p.qk_norm = (g_fa_fast_poly >= 0) ? qk_norm_ws : nullptr;
-  static bool configured = false;
-  if (!configured) {
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<0, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<3, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kernel<5, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, Smem::total));
-    configured = true;
-  }
-  const int grid = p.n_items < sm_count() ? p.n_items : sm_count();
   cudaStream_t st = (cudaStream_t)stream;
   if (p.qk_norm != nullptr) {
     // classify the heads (bounded scores -> max-free kernel), then run both kernels over the item list: each skips the
@@ -839,23 +951,9 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
     attn_qk_norm_kernel<<<dim3(64, 2 * num_heads), 256, 0, st>>>((const __nv_bfloat16*)q, ldq, (int)Lq, (const __nv_bfloat16*)k, ldk,
                                                                  (int)Lk, num_heads, qk_norm_ws);
     B200Q_CHECK_LAUNCH();
-    switch (g_fa_fast_poly) {
-      case 0: attn_bf16_kernel<0, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-      case 1: attn_bf16_kernel<1, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-      case 2: attn_bf16_kernel<2, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-      case 5: attn_bf16_kernel<5, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-      case 4: attn_bf16_kernel<4, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-      default: attn_bf16_kernel<3, true><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    }
-    B200Q_CHECK_LAUNCH();
+    if ((rc = launch_fa_any(true, g_fa_fast_poly, cl, tq, tk, tv, p, st))) return rc;
   }
-  switch (g_fa_mode & 3) {
-    case 0: attn_bf16_kernel<0, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 1: attn_bf16_kernel<1, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    case 3: attn_bf16_kernel<3, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-    default: attn_bf16_kernel<2, false><<<grid, THREADS, Smem::total, st>>>(tq, tk, tv, p); break;
-  }
-  B200Q_CHECK_LAUNCH();
+  if ((rc = launch_fa_any(false, g_fa_mode & 3, cl, tq, tk, tv, p, st))) return rc;
   if (p.n_splits > 1) {
     const long long vecs = Lq * (D / 8);
     attn_merge_kernel<<<(unsigned)((vecs + 255) / 256), 256, 0, st>>>((const __nv_bfloat16*)part_ws, p.split_stride, (int)D, lse_ws,
