@@ -263,12 +263,17 @@ B200Q_API int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads);
  * degree-4 polynomial exp2 on the FMA pipe instead of MUFU.EX2 (0..3, default 2 = 25 %; P within 7e-6 relative, far below
  * its bf16 rounding). */
 B200Q_API int b200q_attn_bf16_set_mode(int mode);
-/* Max-free kernel of b200q_attn_bf16 (bounded heads): polynomial pairs of every 8 (0..5, default 3 - the fastest under the
- * power cap: 5.48 ms at H=12, L=32760 sustained, against 6.31 ms for the online softmax); -1 disables the max-free kernel (every head takes the online softmax even when qk_norm_ws is given). */
+/* Max-free kernels of b200q_attn_bf16 (bounded heads): polynomial pairs of every 8 (0..5); -2 (default) = the measured
+ * best of the kernel in use (key-pipelined: 1, two-tile: 3); -1 disables the max-free kernels (every head takes the online
+ * softmax even when qk_norm_ws is given). */
 B200Q_API int b200q_attn_bf16_set_fast(int poly_pairs);
 /* CTAs per work item of b200q_attn_bf16: 2 (default) = CTA pairs, 512 queries per item, tcgen05.mma.cta_group::2 with each
  * CTA staging half of every K and V tile; 1 = single CTAs, 256 queries per item.  Same function either way. */
 B200Q_API int b200q_attn_bf16_set_cluster(int ctas);
+/* Kernel the bounded (max-free) heads of b200q_attn_bf16 take: 1 (default) = key-pipelined kernel - one 128-row Q tile per
+ * CTA, three S/P buffers in tensor memory, three key blocks in flight, CTA pairs; 0 = the two-tile kernel that also
+ * serves the online-softmax heads.  Same function either way. */
+B200Q_API int b200q_attn_bf16_set_variant(int variant);
 
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the

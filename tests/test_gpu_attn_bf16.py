@@ -150,7 +150,7 @@ def test_attn_bf16_max_free_kernel_equals_online_softmax(dev, poly):
         b200q.attn_bf16_set_fast(poly)
         fast, lse_f = b200q.attn_bf16(q, k, v, H, want_lse=True)
     finally:
-        b200q.attn_bf16_set_fast(3)
+        b200q.attn_bf16_set_fast(-2)
     ref, lse_ref = _ref(q, k, v, H)
     _check(fast, ref)
     _check(online, ref)
@@ -168,3 +168,33 @@ def test_attn_bf16_nan_and_huge_inputs_take_the_online_kernel(dev):
     out = b200q.attn_bf16(q, k, v, H)
     assert torch.isfinite(out.float()).all()
     _check(out, _ref(q, k, v, H)[0], tol=3e-2)
+
+
+@pytest.mark.parametrize("variant,cl", [(0, 1), (0, 2), (1, 2)])
+@pytest.mark.parametrize("H,Lq,Lk", [(1, 1, 1), (2, 200, 300), (3, 513, 129), (12, 1000, 517), (1, 128, 4096), (2, 77, 2000),
+                                     (3, 5000, 3000)])
+def test_attn_bf16_kernel_variants(dev, variant, cl, H, Lq, Lk):
+    """the three kernels behind b200q_attn_bf16 - two-tile on single CTAs, two-tile on CTA pairs (cta_group::2), Q-resident
+    on CTA pairs - compute the same function: each against fp32 softmax attention (output and log-sum-exp), with and
+    without key splits, partial last key block, rows beyond Lq, one key block, odd block counts"""
+    g = torch.Generator(device="cuda").manual_seed(H * 1000 + Lq + Lk)
+    q, k, v = (torch.randn(n, H * 128, device=dev, generator=g).to(torch.bfloat16) for n in (Lq, Lk, Lk))
+    ref, lse_ref = _ref(q, k, v, H)
+    try:
+        b200q.attn_bf16_set_cluster(cl)
+        b200q.attn_bf16_set_variant(variant)
+        out, lse = b200q.attn_bf16(q, k, v, H, want_lse=True)
+        again = b200q.attn_bf16(q, k, v, H, n_splits=1)
+        split = b200q.attn_bf16(q, k, v, H, n_splits=2) if Lk >= 2000 else None
+        b200q.attn_bf16_set_fast(-1)                                # every head through the online-softmax kernel
+        online = b200q.attn_bf16(q, k, v, H)
+    finally:
+        b200q.attn_bf16_set_fast(-2)
+        b200q.attn_bf16_set_cluster(2)
+        b200q.attn_bf16_set_variant(1)
+    _check(out, ref)
+    _check(online, ref)
+    assert torch.allclose(lse, lse_ref, atol=2e-3, rtol=1e-4)
+    assert torch.equal(out, again)
+    if split is not None:
+        _check(split, ref)

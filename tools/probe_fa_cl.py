@@ -16,10 +16,16 @@ def ref(q, k, v, H):
     return (p @ vh).permute(1, 0, 2).reshape(Lq, D)
 
 
+CONFIGS = [("two-tile cl=1", 0, 1), ("two-tile cl=2", 0, 2), ("key-pipelined", 1, 2)]
+if "--new" in sys.argv:
+    CONFIGS = CONFIGS[1:]
+if "--kp" in sys.argv:
+    CONFIGS = CONFIGS[2:]
 ok = True
-for cl in (1, 2):
+for name, variant, cl in ([] if "--nocheck" in sys.argv else CONFIGS):
     b200q.attn_bf16_set_cluster(cl)
-    for fast in (3, -1):
+    b200q.attn_bf16_set_variant(variant)
+    for fast in ((3,) if variant else (3, -1)):
         b200q.attn_bf16_set_fast(fast)
         for (H, Lq, Lk) in [(1, 128, 128), (2, 256, 128), (2, 200, 300), (1, 1, 1), (3, 513, 129), (12, 1000, 517), (2, 512, 1024),
                             (1, 128, 4096), (4, 3000, 512), (2, 77, 2000), (3, 5000, 3000)]:
@@ -34,7 +40,7 @@ for cl in (1, 2):
                 err = float((o - r).abs().max() / r.abs().max())
                 good = err <= 2e-2
                 ok &= good
-                print(f"cl={cl} fast={fast:2d} H={H:2d} Lq={Lq:5d} Lk={Lk:5d} splits={S}  rel err {err:.2e}  {'ok' if good else 'FAIL'}", flush=True)
+                print(f"{name} fast={fast:2d} H={H:2d} Lq={Lq:5d} Lk={Lk:5d} splits={S}  rel err {err:.2e}  {'ok' if good else 'FAIL'}", flush=True)
 b200q.attn_bf16_set_fast(3)
 if not ok:
     sys.exit("correctness FAILED")
@@ -93,17 +99,19 @@ def run(name, fn, secs=2.5):
 
 
 quick = "--quick" in sys.argv
-for cl in (1, 2):
+for name, variant, cl in CONFIGS:
     b200q.attn_bf16_set_cluster(cl)
-    for pp in ((3,) if quick else (2, 3, 4)):
+    b200q.attn_bf16_set_variant(variant)
+    for pp in ((3,) if quick else ((0, 1, 2, 3) if "--lowpoly" in sys.argv else (2, 3, 4))):
         b200q.attn_bf16_set_fast(pp)
-        burst(f"cl={cl} max-free poly {pp}/8", lambda: b200q.attn_bf16(q, k, v, H))
-        run(f"cl={cl} max-free poly {pp}/8", lambda: b200q.attn_bf16(q, k, v, H))
-    b200q.attn_bf16_set_fast(-1)
-    run(f"cl={cl} online softmax", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
+        burst(f"{name} max-free poly {pp}/8", lambda: b200q.attn_bf16(q, k, v, H))
+        run(f"{name} max-free poly {pp}/8", lambda: b200q.attn_bf16(q, k, v, H))
+    if not variant:
+        b200q.attn_bf16_set_fast(-1)
+        run(f"{name} online softmax", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
     b200q.attn_bf16_set_mode(10)
-    burst(f"cl={cl} diag: tensor pipeline alone", lambda: b200q.attn_bf16(q, k, v, H))
-    run(f"cl={cl} diag: tensor pipeline alone", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
+    burst(f"{name} diag: tensor pipeline alone", lambda: b200q.attn_bf16(q, k, v, H))
+    run(f"{name} diag: tensor pipeline alone", lambda: b200q.attn_bf16(q, k, v, H), 2.0)
     b200q.attn_bf16_set_mode(2); b200q.attn_bf16_set_fast(3)
 burst("library SDPA (cuDNN)", lambda: M.sdpa(q, k, v, H))
 run("library SDPA (cuDNN)", lambda: M.sdpa(q, k, v, H))

@@ -68,6 +68,7 @@ _SIGNATURES = {
                                 c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b200q_attn_bf16_set_fast": (c_int, [c_int]),
     "b200q_attn_bf16_set_cluster": (c_int, [c_int]),
+    "b200q_attn_bf16_set_variant": (c_int, [c_int]),
     "b200q_attn_bf16_splits": (c_int, [c_int64, c_int64, c_int]),
     "b200q_rmsnorm_rope_quant": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p,
                                          c_int, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int, c_void_p]),
@@ -456,6 +457,12 @@ def attn_bf16_set_cluster(ctas):
     """1 = single-CTA work items, 2 = CTA pairs with tcgen05.mma.cta_group::2 (default)."""
     if load().b200q_attn_bf16_set_cluster(int(ctas)) != 0:
         raise B200QError("b200q_attn_bf16_set_cluster: 1 or 2")
+
+
+def attn_bf16_set_variant(variant):
+    """Bounded heads: 1 = key-pipelined kernel (default), 0 = two-tile kernel."""
+    if load().b200q_attn_bf16_set_variant(int(variant)) != 0:
+        raise B200QError("b200q_attn_bf16_set_variant: 0 or 1")
 
 
 def attn_bf16_set_mode(mode):

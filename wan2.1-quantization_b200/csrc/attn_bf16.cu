@@ -748,6 +748,309 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   if (warp == W_TMA) { if (CL == 2) tmem_dealloc_2sm<512>(tmem_base); else tmem_dealloc<512>(tmem_base); }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Key-pipelined kernel for bounded heads (max-free softmax), CTA pairs.
+//
+// The two-tile kernel above runs each Q tile through the chain  S(j) -> softmax(j) -> P.V(j) -> S(j+1): P aliases S, so the
+// next Q.K^T of a tile cannot be issued before the tile's P.V, and the tensor pipe idles whenever softmax + handshakes of
+// one tile outlast the other tile's two products (ncu: tensor pipe 78 % active; softmax warps issue 47 % of the cycles:
+// neither side is saturated, each waits for the other).  Without a running maximum nothing in the softmax of key block
+// j+1 depends on block j, so this kernel pipelines over KEY BLOCKS instead of Q tiles and keeps THREE of them in flight:
+//   * one 128-row Q tile per CTA (256 queries per pair), three S/P buffers in TMEM, key block j lives in buffer j mod 3;
+//   * the MMA warp issues  S(0) S(1) S(2) | P.V(0) S(3) | P.V(1) S(4) | ... : P.V(j) is issued two Q.K^T periods after S(j)
+//     completed, so a softmax group has two full (Q.K^T + P.V) periods for a block before the tensor pipe could wait for it;
+//   * softmax group g (8 warps, two threads per row) takes the key blocks j = g mod 2, whatever buffer they are in;
+//   * each CTA stages its own Q tile, half of every K tile (64 keys) and half of every V tile (64 head_dim columns).
+// TMEM columns: [S0/P0 | S1/P1 | S2/P2 | O], 128 each.
+// ---------------------------------------------------------------------------------------------------------------------
+struct SmemKP {
+  static constexpr int ks = 5, vs = 5;
+  static constexpr int ktile = TILE / 2, vtile = TILE / 2, khalf = HALF / 2;
+  static constexpr int q = 0;                          // one 128 x 128 tile
+  static constexpr int k = q + TILE;
+  static constexpr int v = k + ks * ktile;
+  static constexpr int xch = v + vs * vtile;           // [parity][group * 2 + half][row] fp32 partial row sums
+  static constexpr int bar = xch + 2 * 4 * 128 * 4;
+  static constexpr int total = bar + 512;
+};
+static_assert(SmemKP::total <= 232448, "dynamic smem budget (227 KB) exceeded");
+
+template <int POLY>
+__global__ void __launch_bounds__(THREADS, 1)
+attn_bf16_kp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                    const __grid_constant__ CUtensorMap tm_v, const Params p) {
+  using Smem = SmemKP;
+  constexpr int KS = Smem::ks, VS = Smem::vs;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("b200q: dynamic smem base not 1024-byte aligned\n");
+    __trap();
+  }
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Smem::bar);
+  uint64_t* k_full = bars;                 // KS   (leader: bytes of both CTAs' halves)
+  uint64_t* k_empty = k_full + KS;         // KS   (multicast commit)
+  uint64_t* v_full = k_empty + KS;         // VS
+  uint64_t* v_empty = v_full + VS;         // VS
+  uint64_t* s_full = v_empty + VS;         // [buffer]: S(j) complete in TMEM (multicast commit)
+  uint64_t* p_full = s_full + 3;           // [buffer]: P(j) written by both CTAs' softmax group (leader)
+  uint64_t* q_full = p_full + 3;           // Q tiles of the item landed in both CTAs (leader)
+  uint64_t* q_empty = q_full + 1;          // last Q.K^T of the item complete (multicast commit)
+  uint64_t* o_full = q_empty + 1;          // O accumulator of the item complete (multicast commit)
+  uint64_t* o_free = o_full + 1;           // O read out by both CTAs (leader)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(o_free + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nb_all = (p.Lk + BKEY - 1) / BKEY;
+  const int per_head = p.n_qt * p.n_splits;              // item -> (head, key split, 256-query group); rank -> its 128 rows
+  const int rank = (int)cluster_ctarank();
+  const int item0 = (int)blockIdx.x / 2, item_step = (int)gridDim.x / 2;
+  constexpr uint16_t kPair = 3;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < KS; ++i) { mbar_init(&k_full[i], 1); mbar_init(&k_empty[i], 1); }
+    for (int i = 0; i < VS; ++i) { mbar_init(&v_full[i], 1); mbar_init(&v_empty[i], 1); }
+    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 16); }
+    mbar_init(q_full, 1); mbar_init(q_empty, 1);
+    mbar_init(o_full, 1); mbar_init(o_free, 32);
+    fence_barrier_init();
+  }
+  constexpr int W_TMA = 16, W_MMA = 17;
+  if (warp == W_TMA && lane == 0) { prefetch_tmap(&tm_q); prefetch_tmap(&tm_k); prefetch_tmap(&tm_v); }
+  if (warp == W_TMA) tmem_alloc_2sm<512>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  constexpr uint32_t COL_O = 384;
+
+  if (warp == W_TMA) {
+    // ===================== TMA producer: my Q tile, my half of every K tile (64 keys) and V tile (64 head_dim columns) ==========
+    if (lane == 0) {
+      int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
+      for (int item = item0; item < p.n_items; item += item_step) {
+        const int h = item / per_head, sp = (item % per_head) / p.n_qt, q0 = (item % p.n_qt) * (2 * BQ) + rank * BQ;
+        if (!head_is_bounded(p, h)) continue;                             // the online-softmax kernel's head
+        const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
+        bar_wait(q_empty, (it & 1) ^ 1);
+        ++it;
+        {
+          const uint32_t lead = mapa_u32(q_full, 0);
+          if (rank == 0) mbar_expect_tx(q_full, 2 * TILE);
+          tma_load_2d_2sm(smem + Smem::q, &tm_q, lead, h * HD, q0);
+          tma_load_2d_2sm(smem + Smem::q + HALF, &tm_q, lead, h * HD + 64, q0);
+        }
+        for (int j = 0; j < nb; ++j) {
+          bar_wait(&k_empty[ks], kph ^ 1);
+          {
+            const uint32_t lead = mapa_u32(&k_full[ks], 0);
+            if (rank == 0) mbar_expect_tx(&k_full[ks], TILE);
+            tma_load_2d_2sm(smem + Smem::k + ks * Smem::ktile, &tm_k, lead, h * HD, (kb0 + j) * BKEY + rank * 64);
+            tma_load_2d_2sm(smem + Smem::k + ks * Smem::ktile + Smem::khalf, &tm_k, lead, h * HD + 64, (kb0 + j) * BKEY + rank * 64);
+          }
+          if (++ks == KS) { ks = 0; kph ^= 1; }
+          bar_wait(&v_empty[vs], vph ^ 1);
+          {
+            const uint32_t lead = mapa_u32(&v_full[vs], 0);
+            if (rank == 0) mbar_expect_tx(&v_full[vs], TILE);
+            tma_load_2d_2sm(smem + Smem::v + vs * Smem::vtile, &tm_v, lead, h * HD + rank * 64, (kb0 + j) * BKEY);
+          }
+          if (++vs == VS) { vs = 0; vph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == W_MMA) {
+    if (rank == 0) {
+      // ===================== MMA issuer (leader CTA, uniform control flow, one elected lane issues) =====================
+      constexpr uint32_t idesc_qk = idesc_bf16(2 * BQ, BKEY, false);
+      constexpr uint32_t idesc_pv = idesc_bf16(2 * BQ, HD, true);
+      int ks = 0, vs = 0; uint32_t kph = 0, vph = 0; int it = 0;
+      uint32_t ppar = 0;                                     // bit b: parity of p_full[b]'s next phase
+      const uint64_t qd = make_kmajor_sw128_desc(smem_u32(smem + Smem::q));
+      const uint64_t kd = make_kmajor_sw128_desc(smem_u32(smem + Smem::k));
+      const uint64_t vd = make_mnmajor_sw128_desc(smem_u32(smem + Smem::v), HALF, 1024);
+      auto commit = [&](uint64_t* bar) {
+        if (elect_one()) mma_commit_2sm_mc(bar, kPair);
+        __syncwarp();
+      };
+      // S[buf] = Q . K(stage)^T : 8 x (M256, N128, K16)
+      auto qk = [&](int buf) {
+        bar_wait(&k_full[ks], kph);
+        tcgen05_fence_after();
+        const uint64_t b0 = kd + (uint64_t)(ks * (Smem::ktile >> 4));
+        const uint32_t d = tmem_base + buf * 128;
+        if (elect_one()) {
+          if (!(p.mode & 16)) {
+#pragma unroll
+            for (int kk = 0; kk < HD / 16; ++kk) {
+              const uint64_t aoff = (uint64_t)((kk >> 2) * (HALF >> 4) + (kk & 3) * 2);
+              const uint64_t boff = (uint64_t)((kk >> 2) * (Smem::khalf >> 4) + (kk & 3) * 2);
+              mma_bf16_ss_2sm(d, qd + aoff, b0 + boff, idesc_qk, kk != 0 ? 1u : 0u);
+            }
+          }
+          mma_commit_2sm_mc(&s_full[buf], kPair);
+          mma_commit_2sm_mc(&k_empty[ks], kPair);
+        }
+        __syncwarp();
+        if (++ks == KS) { ks = 0; kph ^= 1; }
+      };
+      // O (+)= P[buf] (TMEM; each half-row thread's 64 keys in the first 32 of its own 64 S columns) . V(stage)
+      auto pv = [&](int buf, bool first) {
+        bar_wait_crit(&p_full[buf], (ppar >> buf) & 1u, p.mode);
+        ppar ^= 1u << buf;
+        bar_wait(&v_full[vs], vph);
+        tcgen05_fence_after();
+        const uint64_t b0 = vd + (uint64_t)(vs * (Smem::vtile >> 4));
+        const uint32_t d = tmem_base + COL_O, pa = tmem_base + buf * 128;
+        if (elect_one()) {
+          if (!(p.mode & 16)) {
+#pragma unroll
+            for (int kk = 0; kk < BKEY / 16; ++kk)
+              mma_bf16_ts_2sm(d, pa + (kk >> 2) * 64 + (kk & 3) * 8, b0 + (uint64_t)(kk * (2048 >> 4)), idesc_pv, (first && kk == 0) ? 0u : 1u);
+          }
+          mma_commit_2sm_mc(&v_empty[vs], kPair);
+        }
+        __syncwarp();
+        if (++vs == VS) { vs = 0; vph ^= 1; }
+      };
+      for (int item = item0; item < p.n_items; item += item_step, ++it) {
+        if (!head_is_bounded(p, item / per_head)) { --it; continue; }
+        const int nb = min(p.bps, nb_all - ((item % per_head) / p.n_qt) * p.bps);
+        bar_wait(q_full, it & 1);
+        qk(0);
+        if (nb > 1) qk(1);
+        if (nb > 2) qk(2);
+        if (nb <= 3) commit(q_empty);
+        bar_wait(o_free, it & 1);                              // previous item's O has been read out
+        int buf = 0;
+        for (int j = 0; j < nb; ++j) {
+          pv(buf, j == 0);
+          if (j + 3 < nb) {
+            qk(buf);                                           // in order behind P.V(j), which read this buffer's P
+            if (j + 3 == nb - 1) commit(q_empty);
+          }
+          if (++buf == 3) buf = 0;
+        }
+        commit(o_full);
+      }
+    }
+  } else {
+    // ===================== softmax warps: group g takes key blocks j = g mod 2; thread = (query row, half of the key block) =====
+    const int g = warp >> 3, half = (warp >> 2) & 1, quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const uint32_t t_s0 = tmem_base + half * 64 + lane_off;                // my 64 S columns of buffer 0; P goes into the first 32
+    const uint32_t t_o = tmem_base + COL_O + (g * 2 + half) * 32 + lane_off;   // my 32 O columns at read-out
+    float* xch = reinterpret_cast<float*>(smem + Smem::xch);
+    const uint32_t pf_addr0 = mapa_u32(&p_full[0], 0), of_addr = mapa_u32(o_free, 0);
+    uint32_t itn = 0, xp = 0, bpar = 0;                                    // bpar bit b: parity of s_full[b] at the item's start
+    const float c = p.scale_log2e;
+    const uint64_t c2 = pack_f32x2(c, c);
+    const int tail = p.Lk - (nb_all - 1) * BKEY;
+    {                                                                      // O columns start out free
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(of_addr);
+    }
+    for (int item = item0; item < p.n_items; item += item_step, ++itn) {
+      const int h = item / per_head, sp = (item % per_head) / p.n_qt;
+      if (!head_is_bounded(p, h)) { --itn; continue; }
+      const int kb0 = sp * p.bps, nb = min(p.bps, nb_all - kb0);
+      const int row = (item % p.n_qt) * (2 * BQ) + rank * BQ + r;
+      const bool row_ok = row < p.Lq;
+      uint64_t sum2 = pack_f32x2(0.f, 0.f);
+      int buf = g, use = 0;                                                // key block j lives in buffer j mod 3, its (j / 3)-th use
+      for (int j = g; j < nb; j += 2) {
+        bar_wait_crit(&s_full[buf], ((bpar >> buf) ^ (uint32_t)use) & 1u, p.mode);
+        tcgen05_fence_after();
+        const uint32_t t_s = t_s0 + buf * 128;
+        const uint32_t pf_addr = pf_addr0 + buf * 8;
+        buf += 2; if (buf >= 3) { buf -= 3; ++use; }                       // (j + 2) mod 3, (j + 2) / 3
+        if (p.mode & 8) {                                                  // diagnostic: tensor / TMA pipeline alone
+          tcgen05_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(pf_addr);
+          continue;
+        }
+        uint32_t sa[2][16], sb[2][16];
+        tmem_ld_32x16(t_s, sa[0]);
+        tmem_ld_32x16(t_s + 16, sa[1]);
+        tmem_ld_wait();
+        tmem_ld_32x16(t_s + 32, sb[0]);                                    // in flight during the first half's exponentials
+        tmem_ld_32x16(t_s + 48, sb[1]);
+        uint32_t pk[16];
+        if (kb0 + j == nb_all - 1 && tail < BKEY) {                        // last, partial key block: -inf -> MUFU path gives P = 0
+          tmem_ld_wait();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) {
+            if (half * 64 + e >= tail) sa[0][e] = 0xff800000u;
+            if (half * 64 + 16 + e >= tail) sa[1][e] = 0xff800000u;
+            if (half * 64 + 32 + e >= tail) sb[0][e] = 0xff800000u;
+            if (half * 64 + 48 + e >= tail) sb[1][e] = 0xff800000u;
+          }
+          exp_chunk_fast<0>(sa[0], pk, c2, sum2);
+          exp_chunk_fast<0>(sa[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_s, pk);
+          exp_chunk_fast<0>(sb[0], pk, c2, sum2);
+          exp_chunk_fast<0>(sb[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_s + 16, pk);
+        } else {
+          exp_chunk_fast<POLY>(sa[0], pk, c2, sum2);
+          exp_chunk_fast<POLY>(sa[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_s, pk);
+          tmem_ld_wait();
+          exp_chunk_fast<POLY>(sb[0], pk, c2, sum2);
+          exp_chunk_fast<POLY>(sb[1], pk + 8, c2, sum2);
+          tmem_st_32x16(t_s + 16, pk);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(pf_addr);
+      }
+      // buffer b was used (nb + 2 - b) / 3 times by this item
+      bpar ^= (uint32_t)(((nb + 2) / 3) & 1) | (uint32_t)((((nb + 1) / 3) & 1) << 1) | (uint32_t)(((nb / 3) & 1) << 2);
+      // ---- read-out: out = O / l, l = the four partial sums of the row (two groups x two halves) ----
+      float s0, s1;
+      unpack_f32x2(sum2, s0, s1);
+      xch[xp * 512 + (g * 2 + half) * 128 + r] = s0 + s1;
+      named_bar_sync(1, 512);
+      const float* xr = xch + xp * 512 + r;
+      const float l = (xr[0] + xr[128]) + (xr[256] + xr[384]);
+      xp ^= 1;
+      const float inv = 1.0f / l;
+      bar_wait(o_full, itn & 1);
+      tcgen05_fence_after();
+      if (g == 0 && half == 0 && row_ok && p.lse_out != nullptr) p.lse_out[((long long)sp * p.H + h) * p.Lq + row] = log2f(l);
+      uint32_t o[32];
+      tmem_ld_32x16(t_o, o);
+      tmem_ld_32x16(t_o + 16, o + 16);
+      tmem_ld_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(of_addr);                         // O is in registers: hand the columns back
+      if (row_ok) {
+        __nv_bfloat16* dst = p.out + sp * p.split_stride + (long long)row * p.ldo + h * HD + (g * 2 + half) * 32;
+#pragma unroll
+        for (int e = 0; e < 32; e += 8) {
+          uint4 w;
+          w.x = pack_bf16x2(__uint_as_float(o[e]) * inv, __uint_as_float(o[e + 1]) * inv);
+          w.y = pack_bf16x2(__uint_as_float(o[e + 2]) * inv, __uint_as_float(o[e + 3]) * inv);
+          w.z = pack_bf16x2(__uint_as_float(o[e + 4]) * inv, __uint_as_float(o[e + 5]) * inv);
+          w.w = pack_bf16x2(__uint_as_float(o[e + 6]) * inv, __uint_as_float(o[e + 7]) * inv);
+          *reinterpret_cast<uint4*>(dst + e) = w;
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  cluster_sync();
+  tcgen05_fence_after();
+  if (warp == W_TMA) tmem_dealloc_2sm<512>(tmem_base);
+}
+
 // Per-head maxima of the squared row norms: norms[h] = max_i |q_i,h|^2 (blockIdx.y = h), norms[H + h] = max_j |k_j,h|^2
 // (blockIdx.y = H + h).  16 lanes read one 256-byte head slice of a row (16 B each); one atomicMax per CTA (the values
 // are non-negative, so the integer order of the bit patterns is the float order).  norms must be zeroed before.
@@ -826,7 +1129,9 @@ using namespace b200q;
 // TMA / shared-memory pipeline alone), +16 = the MMA warp walks its schedule without issuing (the softmax warps alone),
 // +32 = softmax warps stop after the TMEM load, row maximum and exchange.
 static int g_fa_mode = 2;
-static int g_fa_fast_poly = 3;      // max-free kernel: polynomial pairs of every 8 (0..5); -1 = never use the max-free kernel
+// max-free kernels: polynomial pairs of every 8 (0..5); -1 = never use a max-free kernel; -2 = not set: the measured best of
+// each kernel (two-tile: 3, key-pipelined: 1 - with three key blocks in flight the MUFU is no longer on a critical chain)
+static int g_fa_fast_poly = -2;
 static int g_fa_cl = 2;             // CTAs per cluster: 2 = CTA pairs with tcgen05.mma.cta_group::2 (default), 1 = single CTAs
 extern "C" int b200q_attn_bf16_set_mode(int mode) {
   if (mode < 0 || mode > 255 || (mode & 4)) return B200Q_ERR_BAD_ARG;
@@ -834,13 +1139,19 @@ extern "C" int b200q_attn_bf16_set_mode(int mode) {
   return B200Q_OK;
 }
 extern "C" int b200q_attn_bf16_set_fast(int poly_pairs) {
-  if (poly_pairs < -1 || poly_pairs > 5) return B200Q_ERR_BAD_ARG;
+  if (poly_pairs < -2 || poly_pairs > 5) return B200Q_ERR_BAD_ARG;
   g_fa_fast_poly = poly_pairs;
   return B200Q_OK;
 }
+static int g_fa_kp = 1;             // bounded heads: 1 = key-pipelined kernel (three key blocks in flight), 0 = two-tile kernel
 extern "C" int b200q_attn_bf16_set_cluster(int ctas) {
   if (ctas != 1 && ctas != 2) return B200Q_ERR_BAD_ARG;
   g_fa_cl = ctas;
+  return B200Q_OK;
+}
+extern "C" int b200q_attn_bf16_set_variant(int variant) {
+  if (variant != 0 && variant != 1) return B200Q_ERR_BAD_ARG;
+  g_fa_kp = variant;
   return B200Q_OK;
 }
 
@@ -850,8 +1161,12 @@ extern "C" int b200q_attn_bf16_set_cluster(int ctas) {
 extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
   using namespace fa;
   if (Lq <= 0 || Lk <= 0 || num_heads <= 0) return 1;
-  const int cl = g_fa_cl;                                             // items are walked by clusters of cl CTAs
-  const long long items = ((Lq + 2 * BQ * cl - 1) / (2 * BQ * cl)) * num_heads;
+  // items are walked by clusters of cl CTAs; the key-pipelined kernel (the one Wan's RMS-normed heads take) works on
+  // 256-query items in CTA pairs, the two-tile kernel on 256 * cl
+  const bool qres = g_fa_kp && g_fa_fast_poly != -1;
+  const int cl = qres ? 2 : g_fa_cl;
+  const int rows = qres ? 2 * BQ : 2 * BQ * cl;
+  const long long items = ((Lq + rows - 1) / rows) * num_heads;
   const int nb = (int)((Lk + BKEY - 1) / BKEY), sms = sm_count() / cl;
   int best = 1;
   double best_cost = 0;
@@ -893,6 +1208,35 @@ static int launch_fa_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk
     case 4: return launch_fa<FAST ? 4 : 3, FAST, CL>(tq, tk, tv, p, st);      // 4 and 5 exist for the max-free kernel only
     case 5: return launch_fa<FAST ? 5 : 3, FAST, CL>(tq, tk, tv, p, st);
     default: return launch_fa<3, FAST, CL>(tq, tk, tv, p, st);
+  }
+}
+template <int POLY>
+static int launch_fa_kp(const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::Params& p, cudaStream_t st) {
+  using namespace fa;
+  static bool configured = false;
+  if (!configured) {
+    B200Q_CUDA_OK(cudaFuncSetAttribute(attn_bf16_kp_kernel<POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemKP::total));
+    configured = true;
+  }
+  const int cap = (sm_count() / 2) * 2;
+  const int grid = p.n_items * 2 < cap ? p.n_items * 2 : cap;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(THREADS); cfg.dynamicSmemBytes = SmemKP::total; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  B200Q_CUDA_OK(cudaLaunchKernelEx(&cfg, attn_bf16_kp_kernel<POLY>, tq, tk, tv, p));
+  return B200Q_OK;
+}
+static int launch_fa_kp_poly(int poly, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv, const fa::Params& p, cudaStream_t st) {
+  switch (poly) {
+    case 0: return launch_fa_kp<0>(tq, tk, tv, p, st);
+    case 1: return launch_fa_kp<1>(tq, tk, tv, p, st);
+    case 2: return launch_fa_kp<2>(tq, tk, tv, p, st);
+    case 4: return launch_fa_kp<4>(tq, tk, tv, p, st);
+    case 5: return launch_fa_kp<5>(tq, tk, tv, p, st);
+    default: return launch_fa_kp<3>(tq, tk, tv, p, st);
   }
 }
 static int launch_fa_any(bool fast, int poly, int cl, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
@@ -942,7 +1286,7 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   }
   p.n_items = p.n_qt * num_heads * p.n_splits;
   p.mode = g_fa_mode;
-  p.qk_norm = (g_fa_fast_poly >= 0) ? qk_norm_ws : nullptr;
+  p.qk_norm = (g_fa_fast_poly != -1) ? qk_norm_ws : nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   if (p.qk_norm != nullptr) {
     // classify the heads (bounded scores -> max-free kernel), then run both kernels over the item list: each skips the
@@ -951,7 +1295,15 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
     attn_qk_norm_kernel<<<dim3(64, 2 * num_heads), 256, 0, st>>>((const __nv_bfloat16*)q, ldq, (int)Lq, (const __nv_bfloat16*)k, ldk,
                                                                  (int)Lk, num_heads, qk_norm_ws);
     B200Q_CHECK_LAUNCH();
-    if ((rc = launch_fa_any(true, g_fa_fast_poly, cl, tq, tk, tv, p, st))) return rc;
+    if (g_fa_kp) {
+      // bounded heads on the key-pipelined kernel: 256-query items on CTA pairs, K boxes of 64 keys
+      Params pq = p;
+      pq.n_qt = (int)((Lq + 2 * BQ - 1) / (2 * BQ));
+      pq.n_items = pq.n_qt * num_heads * p.n_splits;
+      CUtensorMap tk2 = tk;
+      if (cl != 2 && (rc = make_tmap_2d(&tk2, k, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, Lk, D, ldk, BKEY / 2, 64, CU_TENSOR_MAP_SWIZZLE_128B))) return rc;
+      if ((rc = launch_fa_kp_poly(g_fa_fast_poly == -2 ? 1 : g_fa_fast_poly, tq, tk2, tv, pq, st))) return rc;
+    } else if ((rc = launch_fa_any(true, g_fa_fast_poly == -2 ? 3 : g_fa_fast_poly, cl, tq, tk, tv, p, st))) return rc;
   }
   if ((rc = launch_fa_any(false, g_fa_mode & 3, cl, tq, tk, tv, p, st))) return rc;
   if (p.n_splits > 1) {
