@@ -60,6 +60,8 @@ def parse():
     ap.add_argument("--no-variants", action="store_true", help="skip the extra attention-core timings at N=1")
     ap.add_argument("--no-verify", action="store_true", help="N>1: skip the comparison against the unsharded step")
     ap.add_argument("--max-seconds", type=float, default=900.0, help="watchdog: hard-exit after this wall-clock time")
+    ap.add_argument("--exchange", default="auto", choices=["auto", "peer", "nccl"],
+                    help="N>1: attention exchange over NVLink peer memory (b200q_scatter_rows + barrier) or NCCL send/recv")
     ap.add_argument("--pipeline-chunks", type=int, default=0,
                     help="N>1: exchange/attend the heads of a rank's head group in this many chunks (exchange overlaps "
                          "attention); 0 = auto")
@@ -335,7 +337,7 @@ def run_b200(args):
         from wan_b200.parallel import _largest_head_divisor
         hg = cfg.num_heads // _largest_head_divisor(world, cfg.num_heads)         # heads per head group
         args.pipeline_chunks = 3 if hg % 3 == 0 else (2 if hg % 2 == 0 else 1)
-    sp = SequenceParallel(pipeline_chunks=args.pipeline_chunks) if world > 1 else None
+    sp = SequenceParallel(pipeline_chunks=args.pipeline_chunks, exchange=args.exchange) if world > 1 else None
     dit = M.WanDiTQ.random(cfg, seed=0, sp=sp, num_layers=args.layers, attn_quant=(attn == "int8"), ffn_bits=args.ffn_bits)
     L = (LATENT_SHAPE[1] // 1) * (LATENT_SHAPE[2] // 2) * (LATENT_SHAPE[3] // 2)
     B = args.cfg_batch
@@ -648,7 +650,10 @@ def run_b200(args):
             b, pu, pr = exchange_bytes_per_rank(L, cfg.dim, world, cfg.num_heads)
             out["config"]["exchange_bytes_per_rank_per_block"] = b
             out["config"]["head_plan"] = f"Pu={pu} x Pr={pr}"
-            out["config"]["pipeline_chunks"] = args.pipeline_chunks
+            out["config"]["exchange"] = sp.exchange_in_use
+            if sp.exchange_fallback:
+                out["config"]["exchange_fallback"] = sp.exchange_fallback
+            out["config"]["pipeline_chunks"] = args.pipeline_chunks if sp.exchange_in_use == "nccl" else 1
         if args.layers is not None and args.layers != cfg.num_layers:
             out["invalid"] = f"debug run with {args.layers} of {cfg.num_layers} blocks"
         if world == 1 and not args.no_cpu_baseline:

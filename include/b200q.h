@@ -275,6 +275,16 @@ B200Q_API int b200q_attn_bf16_set_cluster(int ctas);
  * serves the online-softmax heads.  Same function either way. */
 B200Q_API int b200q_attn_bf16_set_variant(int variant);
 
+/* b200q_scatter_rows: the data movement of the sequence-parallel attention exchange over NVLink peer memory.  Replaces the
+ * Ulysses all-to-alls of examples/Wan2.1/wan/distributed/xdit_context_parallel.py:149-192 (xfuser SeqAllToAll4D: four
+ * all_to_all_single calls per block with a permuting copy on either side).  n messages (<= 48) in ONE launch: message i
+ * copies `rows` rows of `row_bytes` bytes from src[i] (row pitch src_pitch_bytes[i]) to dst[i] (row pitch dst_pitch_bytes);
+ * dst[i] is typically a peer GPU's buffer (a CUDA peer mapping), src[i] a column slice of this rank's q|k|v GEMM output
+ * or attention output.  src / dst / src_pitch_bytes are HOST arrays; everything 16-byte aligned, row_bytes and pitches
+ * multiples of 16.  Ordering against the consumers on the other GPUs is the caller's (one barrier after the launch). */
+B200Q_API int b200q_scatter_rows(const void* const* src, void* const* dst, int n, int64_t rows, int64_t row_bytes,
+                       const int64_t* src_pitch_bytes, int64_t dst_pitch_bytes, b200q_stream_t stream);
+
 /* b200q_attn_i8: fused int8 attention, head_dim = 128.
  *   qq int8 [Lq, H*128] (ldq), kq int8 [Lk, H*128] (ldk): per-(token, head) symmetric codes (b200q_quant_rows on the
  *   [L*H, 128] view); dq/dk: their fp32 scales, element (token, head) at dq[token*dq_tok_stride + head*dq_head_stride];

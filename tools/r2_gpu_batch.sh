@@ -15,6 +15,6 @@ timeout 1200 ncu --set full --clock-control none --profile-from-start off -o /tm
   > gpurun_out/${TAG}_ncu_full.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/prof_${TAG}.ncu-rep --page raw --csv > gpurun_out/prof_${TAG}_raw.csv 2>/dev/null; ls -la /tmp/prof_${TAG}.ncu-rep gpurun_out/prof_${TAG}_raw.csv
 # attention core alone, with source (small report)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bf16_kernel --launch-skip 2 -c 1 -o gpurun_out/fa_${TAG} -f \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:attn_bf16_kp_kernel --launch-skip 2 -c 1 -o gpurun_out/fa_${TAG} -f \
   python tools/run_attn_bf16.py 12 32760 32760 3 > gpurun_out/${TAG}_ncu_fa.log 2>&1; echo "ncu fa rc=$?"
 du -sh gpurun_out

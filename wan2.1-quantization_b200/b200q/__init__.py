@@ -63,6 +63,7 @@ _SIGNATURES = {
                               c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int, c_int, c_float, c_void_p, c_int,
                               c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_attn_set_mode": (c_int, [c_int]),
+    "b200q_scatter_rows": (c_int, [c_void_p, c_void_p, c_int, c_int64, c_int64, c_void_p, c_int64, c_void_p]),
     "b200q_attn_bf16_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
                                 c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
@@ -445,6 +446,20 @@ def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_spl
                                 _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _ptr(norm_ws), _stream())
     _check(rc, "b200q_attn_bf16")
     return (out, lse) if want_lse else out
+
+
+def scatter_rows(src_ptrs, dst_ptrs, rows, row_bytes, src_pitch_bytes, dst_pitch_bytes):
+    """One launch that copies len(src_ptrs) messages of rows x row_bytes: src_ptrs[i] (row pitch src_pitch_bytes[i]) ->
+    dst_ptrs[i] (integer device addresses; the destinations are typically peer-GPU buffers).  The data movement of the
+    sequence-parallel attention exchange."""
+    n = len(src_ptrs)
+    if n != len(dst_ptrs) or n != len(src_pitch_bytes):
+        raise B200QError("scatter_rows: src / dst / pitch lists differ in length")
+    arr = ctypes.c_void_p * max(n, 1)
+    pit = c_int64 * max(n, 1)
+    rc = load().b200q_scatter_rows(arr(*src_ptrs), arr(*dst_ptrs), n, int(rows), int(row_bytes), pit(*src_pitch_bytes),
+                                   int(dst_pitch_bytes), _stream())
+    _check(rc, "b200q_scatter_rows")
 
 
 def attn_bf16_set_fast(poly_pairs):

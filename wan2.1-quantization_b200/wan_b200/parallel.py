@@ -33,11 +33,23 @@ def _largest_head_divisor(world, heads):
 
 
 class SequenceParallel:
-    def __init__(self, group=None, attention_core=None, pipeline_chunks=1):
-        """pipeline_chunks > 1: the heads of a rank's head group are exchanged and attended in that many chunks, so the
-        NCCL transfer of chunk c+1 (and the return of chunk c-1) runs while the attention core works on chunk c
-        (send/recv are asynchronous on NCCL's stream; only the consumer waits).  Results are bit-identical to the
+    def __init__(self, group=None, attention_core=None, pipeline_chunks=1, exchange="auto"):
+        """exchange: how q|k|v and the attention output travel between the ranks.
+          "peer"  one b200q_scatter_rows launch stores every destination's slice straight into that rank's receive buffer
+                  over NVLink (one symmetric allocation per rank, peers mapped as plain device pointers), one signal-pad
+                  barrier before the data is consumed: no staging copies, no NCCL call on the data path;
+          "nccl"  grouped NCCL send/recv (`batch_isend_irecv`) with group-major staging copies;
+          "auto"  "peer" on CUDA with the nccl backend when the symmetric allocation succeeds, else "nccl"
+                  (`exchange_in_use` / `exchange_fallback` say which and why).
+        pipeline_chunks > 1 (nccl exchange only): the heads of a rank's head group are exchanged and attended in that many
+        chunks, so the NCCL transfer of chunk c+1 (and the return of chunk c-1) runs while the attention core works on
+        chunk c (send/recv are asynchronous on NCCL's stream; only the consumer waits).  Results are bit-identical to the
         single-exchange path - attention is independent per head."""
+        if exchange not in ("auto", "peer", "nccl"):
+            raise ValueError(exchange)
+        self.exchange, self.exchange_in_use, self.exchange_fallback = exchange, None, None
+        self._peer = {}
+        self._peer_calls = 0
         self.pipeline_chunks = int(pipeline_chunks)
         self.group = group
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
@@ -121,6 +133,11 @@ class SequenceParallel:
         Pu, Pr, g, h = self.plan(num_heads)
         Hg = num_heads // Pu
         W = Hg * hd
+        if self.exchange != "nccl" and q.is_cuda:
+            peer = self._peer_buffers(Lr, W, P, Pu, q.dtype, q.device)
+            if peer is not None:
+                return self._attention_peer(q, k, v, core, peer, Lr, W, Pu, Pr, g, h, Hg)
+        self.exchange_in_use = "nccl"
         C = self.pipeline_chunks
         if C > 1 and Hg % C == 0:
             return self._attention_pipelined(q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C)
@@ -167,6 +184,77 @@ class SequenceParallel:
             for w in dist.batch_isend_irecv(ops):
                 w.wait()
         return Or.permute(1, 0, 2).reshape(Lr, Pu * W)                          # [Lr, H*hd]
+
+    # ---- exchange over NVLink peer memory --------------------------------------------------------------------
+    def _peer_buffers(self, Lr, W, P, Pu, dtype, device):
+        """One symmetric allocation per rank and shape: [K of all ranks | V of all ranks | Q of my replica | 2 x output],
+        plus every peer's base address.  None (with the reason in `exchange_fallback`) when it cannot be set up."""
+        key = (Lr, W, P, Pu, dtype)
+        if key in self._peer:
+            return self._peer[key]
+        try:
+            if dist.get_backend(self.group) != "nccl":
+                raise RuntimeError("peer-memory exchange needs CUDA ranks on one NVLink domain (backend %s)" % dist.get_backend(self.group))
+            import torch.distributed._symmetric_memory as symm
+            n_k, n_q, n_o = P * Lr * W, Pu * Lr * W, Lr * Pu * W
+            buf = symm.empty(2 * n_k + n_q + 2 * n_o, dtype=dtype, device=device)
+            hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
+            es = buf.element_size()
+            off = {"k": 0, "v": n_k, "q": 2 * n_k, "o0": 2 * n_k + n_q, "o1": 2 * n_k + n_q + n_o}
+            peer = {
+                "hdl": hdl, "buf": buf, "base": [int(p) for p in hdl.buffer_ptrs], "off": {k_: v_ * es for k_, v_ in off.items()},
+                "K": buf[off["k"]:off["k"] + n_k].view(P * Lr, W), "V": buf[off["v"]:off["v"] + n_k].view(P * Lr, W),
+                "Q": buf[off["q"]:off["q"] + n_q].view(Pu * Lr, W),
+                "O": [buf[off["o0"]:off["o0"] + n_o].view(Lr, Pu * W), buf[off["o1"]:off["o1"] + n_o].view(Lr, Pu * W)],
+            }
+            hdl.barrier()
+            self.exchange_in_use = "peer"
+        except Exception as ex:                                   # no NVLink peer mapping here: stay on NCCL, say why
+            if self.exchange == "peer":
+                raise
+            self.exchange_fallback = repr(ex)
+            peer = None
+        self._peer[key] = peer
+        return peer
+
+    def _attention_peer(self, q, k, v, core, peer, Lr, W, Pu, Pr, g, h, Hg):
+        """attention() with both exchanges as direct stores into the peers' buffers (include/b200q.h b200q_scatter_rows).
+        Layout at every destination: K / V of all ranks [P, Lr, W] == [L, W] (slot = sending rank), Q of the replica
+        [Pu, Lr, W] (slot = the sender's place in the replica), output [Lr, Pu * W] (column block = the head group the
+        sender computed) - exactly what the attention kernel and the output projection read, so nothing is repacked.
+        Two barriers per attention: operands landed / outputs landed.  The second one also orders this block's reads of
+        K, V, Q before the next block's stores into them (a rank only reaches it after its own attention kernel)."""
+        import b200q
+        P = self.world_size
+        es = q.element_size()
+        base, off, me = peer["base"], peer["off"], self.rank
+        slot = Lr * W * es
+        src, dst, pitch = [], [], []
+        for dest in range(P):
+            gp, hp = dest % Pu, dest // Pu                    # the destination computes head group gp for replica hp's queries
+            col = gp * W * es
+            for name, t in (("k", k), ("v", v)):
+                src.append(t.data_ptr() + col); dst.append(base[dest] + off[name] + me * slot); pitch.append(t.stride(0) * es)
+            if hp == h:
+                src.append(q.data_ptr() + col); dst.append(base[dest] + off["q"] + g * slot); pitch.append(q.stride(0) * es)
+            if dest != me:
+                self.bytes_sent += (3 if hp == h else 2) * slot
+        b200q.scatter_rows(src, dst, Lr, W * es, pitch, W * es)
+        peer["hdl"].barrier()
+        O = core(peer["Q"], peer["K"], peer["V"], Hg)              # [Pu * Lr, W]: my head group for the replica's queries
+        which = self._peer_calls & 1                                # two output buffers: CFG branches are attended back to back
+        self._peer_calls += 1
+        okey = "o1" if which else "o0"
+        src, dst, pitch = [], [], []
+        for i in range(Pu):                                         # rows i*Lr.. belong to rank h*Pu + i; I computed head group g
+            dest = h * Pu + i
+            src.append(O.data_ptr() + i * Lr * O.stride(0) * es); dst.append(base[dest] + off[okey] + g * W * es)
+            pitch.append(O.stride(0) * es)
+            if dest != me:
+                self.bytes_sent += slot
+        b200q.scatter_rows(src, dst, Lr, W * es, pitch, Pu * W * es)
+        peer["hdl"].barrier()
+        return peer["O"][which]                                     # [Lr, H*hd]
 
     def _attention_pipelined(self, q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C):
         """Head-chunked variant of attention(): the heads of a group travel and are attended in C chunks.  Staging layout
