@@ -46,8 +46,12 @@ constexpr int TMEM_COLS = 512;
 template <bool W4, int NSTAGE, int PAIR>
 struct GemmSmem {
   static constexpr bool mma2 = (PAIR == 2);
-  static constexpr int stages = mma2 ? NSTAGE + 2 : NSTAGE;   // NSTAGE 4 (or 3 with double-buffered staging: short-K gate-residual)
-  static constexpr int staging_bufs = (NSTAGE == 3) ? 2 : 1;
+  // NSTAGE 4, or 3 for the short-K gate-residual GEMMs: their epilogue is bound by the LATENCY of the fp32 residual boxes
+  // (one 4 KB box per warp in flight moves 4.7 MB over the chip per HBM round trip), so they trade ring stages for
+  // staging buffers - two residual boxes in flight per warp with cta_group::2 (half-size B stages), one otherwise
+  static constexpr bool deep = mma2 && !W4 && NSTAGE == 3;
+  static constexpr int stages = mma2 ? (deep ? 4 : NSTAGE + 2) : NSTAGE;
+  static constexpr int staging_bufs = (NSTAGE == 3) ? (deep ? 3 : 2) : 1;
   static constexpr int b_rows = mma2 ? BN / 2 : BN;            // B rows staged per CTA
   static constexpr int b_unpacked = b_rows * BK;
   static constexpr int b_stage = W4 ? b_unpacked / 2 : b_unpacked;
@@ -57,7 +61,7 @@ struct GemmSmem {
   static constexpr int staging = unpack + (W4 ? UNPACK_BUFS * b_unpacked : 0);
   static constexpr int colparams = staging + EPI_WARPS * staging_bufs * STAGING_BYTES;   // dw[BN] f32, bias[BN] f32, zp[BN] i16
   static constexpr int barriers = colparams + BN * 4 + BN * 4 + BN * 2;
-  static constexpr int total = barriers + 256;
+  static constexpr int total = barriers + 384;
   static constexpr int threads = (CTRL_WARPS + EPI_WARPS + (W4 ? CVT_WARPS : 0)) * 32;
   static_assert(total <= 232448, "dynamic smem budget (227 KB) exceeded");
 };
@@ -146,8 +150,8 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full_bar = empty_bar + STAGES;
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-  uint64_t* res_bar = tmem_empty_bar + 2;                      // EPI_WARPS barriers: residual tile landed
-  uint64_t* bready_bar = res_bar + EPI_WARPS;                  // W4: unpacked B tile ready (converter -> MMA)
+  uint64_t* res_bar = tmem_empty_bar + 2;                      // [EPI_WARPS][3]: residual box landed in staging buffer b
+  uint64_t* bready_bar = res_bar + EPI_WARPS * 3;              // W4: unpacked B tile ready (converter -> MMA)
   uint64_t* bfree_bar = bready_bar + UNPACK_BUFS;              // W4: unpacked B tile consumed (MMA -> converter)
   uint32_t* tmem_base_slot = reinterpret_cast<uint32_t*>(bfree_bar + UNPACK_BUFS);
 
@@ -178,7 +182,7 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
       mbar_init(&tmem_full_bar[s], 1);
       mbar_init(&tmem_empty_bar[s], MMA2 ? 2 * EPI_WARPS : EPI_WARPS);   // MMA2: both CTAs' epilogues drain before the leader reuses TMEM
     }
-    for (int s = 0; s < EPI_WARPS; ++s) mbar_init(&res_bar[s], 1);
+    for (int s = 0; s < EPI_WARPS * 3; ++s) mbar_init(&res_bar[s], 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -326,22 +330,30 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
     constexpr bool GATE = (EPI == B200Q_EPI_GATE_RESIDUAL);
     uint8_t* my_staging = smem + SM::staging + ew * NBUF * STAGING_BYTES;
     const int col_base = half * (BN / 2);
-    uint32_t res_phase = 0;
+    uint32_t res_phase = 0;                                  // bit b: parity of res_bar[ew][b]'s next phase
+    int sb = 0;                                              // staging buffer of the current chunk (chunk counter mod NBUF)
+    constexpr int DIST = NBUF - 1;                           // residual boxes in flight per warp
 
-    // residual prefetch (GATE): box [32 rows x CPS cols] of tile `t`, chunk `u` -> staging buffer (u & 1)
+    // residual prefetch (GATE): box [32 rows x CPS cols] of tile `t`, chunk `u` -> staging buffer `b`
     auto box_live = [&](int t, int u) {
       return t < num_tiles && tile_m0(t) + quarter * 32 < p.M && tile_n0(t) + col_base + u * CPS < p.N;
     };
-    auto prefetch_residual = [&](int t, int u) {
+    auto prefetch_residual = [&](int t, int u, int b) {
+      while (u >= CHUNKS) { u -= CHUNKS; t += tile_step; }   // chunk u of tile t, counted on into my next tiles
       if (lane == 0 && box_live(t, u)) {
-        if (NBUF == 2) tma_store_wait_read<1>();             // the store that last read this buffer (2 chunks ago) is done
+        // the store that last read this buffer is done: with NBUF > 1 that is the store of the PREVIOUS chunk (the box goes
+        // DIST chunks ahead into the buffer the chunk before the current one used), so one store may stay outstanding
+        if (NBUF > 1) tma_store_wait_read<1>();
         else tma_store_wait_read<0>();
-        mbar_expect_tx(&res_bar[ew], STAGING_BYTES);
-        tma_load_2d(my_staging + (NBUF == 2 ? (u & 1) : 0) * STAGING_BYTES, &tm_res, &res_bar[ew],
+        mbar_expect_tx(&res_bar[ew * 3 + b], STAGING_BYTES);
+        tma_load_2d(my_staging + b * STAGING_BYTES, &tm_res, &res_bar[ew * 3 + b],
                     tile_n0(t) + col_base + u * CPS, tile_m0(t) + quarter * 32);
       }
     };
-    if (GATE && NBUF == 2) prefetch_residual(first_tile, 0);
+    if (GATE && NBUF > 1) {
+#pragma unroll
+      for (int d = 0; d < DIST; ++d) prefetch_residual(first_tile, d, d);
+    }
 
     int it = 0;
     for (int tile = first_tile; tile < num_tiles; tile += tile_step, ++it) {
@@ -374,12 +386,12 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 
 #pragma unroll 1
       for (int u = 0; u < CHUNKS; ++u) {
-        uint8_t* sbuf_ptr = my_staging + (NBUF == 2 ? (u & 1) : 0) * STAGING_BYTES;
+        uint8_t* sbuf_ptr = my_staging + sb * STAGING_BYTES;
         const bool live = box_live(tile, u);
-        if (GATE && NBUF == 1) prefetch_residual(tile, u);   // long-K variant: no spare buffer, load in place
-        if (GATE && live) {                                  // residual box prefetched one chunk ago has landed
-          mbar_wait(&res_bar[ew], res_phase);
-          res_phase ^= 1;
+        if (GATE && NBUF == 1) prefetch_residual(tile, u, 0);   // long-K variant: no spare buffer, load in place
+        if (GATE && live) {                                  // residual box prefetched DIST chunks ago has landed
+          mbar_wait(&res_bar[ew * 3 + sb], (res_phase >> sb) & 1u);
+          res_phase ^= 1u << sb;
         }
         uint4 o[CPS / ELEMS];                                // this thread's 128-byte output row, packed
 #pragma unroll
@@ -442,9 +454,10 @@ gemm_i8_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
           if (live) tma_store_2d(&tm_out, sbuf_ptr, n0 + col_base + u * CPS, m0 + quarter * 32);
           tma_store_commit();
         }
-        if (GATE && NBUF == 2) {                             // next box: next chunk of this tile, or chunk 0 of my next tile
-          if (u + 1 < CHUNKS) prefetch_residual(tile, u + 1);
-          else prefetch_residual(tile + tile_step, 0);
+        if (GATE && NBUF > 1) {                              // the box DIST chunks ahead (this tile or my next ones) goes into
+          const int pb = sb == 0 ? NBUF - 1 : sb - 1;        // the buffer the previous chunk used
+          prefetch_residual(tile, u + DIST, pb);
+          if (++sb == NBUF) sb = 0;
         }
       }
     }
