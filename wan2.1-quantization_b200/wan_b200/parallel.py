@@ -196,17 +196,10 @@ class SequenceParallel:
             if dist.get_backend(self.group) != "nccl":
                 raise RuntimeError("peer-memory exchange needs CUDA ranks on one NVLink domain (backend %s)" % dist.get_backend(self.group))
             import torch.distributed._symmetric_memory as symm
-            n_k, n_q, n_o = P * Lr * W, Pu * Lr * W, Lr * Pu * W
-            buf = symm.empty(2 * n_k + n_q + 2 * n_o, dtype=dtype, device=device)
+            buf = symm.empty(self.peer_numel(Lr, W, P, Pu), dtype=dtype, device=device)
             hdl = symm.rendezvous(buf, self.group if self.group is not None else dist.group.WORLD)
-            es = buf.element_size()
-            off = {"k": 0, "v": n_k, "q": 2 * n_k, "o0": 2 * n_k + n_q, "o1": 2 * n_k + n_q + n_o}
-            peer = {
-                "hdl": hdl, "buf": buf, "base": [int(p) for p in hdl.buffer_ptrs], "off": {k_: v_ * es for k_, v_ in off.items()},
-                "K": buf[off["k"]:off["k"] + n_k].view(P * Lr, W), "V": buf[off["v"]:off["v"] + n_k].view(P * Lr, W),
-                "Q": buf[off["q"]:off["q"] + n_q].view(Pu * Lr, W),
-                "O": [buf[off["o0"]:off["o0"] + n_o].view(Lr, Pu * W), buf[off["o1"]:off["o1"] + n_o].view(Lr, Pu * W)],
-            }
+            peer = self.peer_layout(buf, Lr, W, P, Pu)
+            peer["hdl"], peer["base"] = hdl, [int(p) for p in hdl.buffer_ptrs]
             hdl.barrier()
             self.exchange_in_use = "peer"
         except Exception as ex:                                   # no NVLink peer mapping here: stay on NCCL, say why
@@ -217,18 +210,11 @@ class SequenceParallel:
         self._peer[key] = peer
         return peer
 
-    def _attention_peer(self, q, k, v, core, peer, Lr, W, Pu, Pr, g, h, Hg):
-        """attention() with both exchanges as direct stores into the peers' buffers (include/b200q.h b200q_scatter_rows).
-        Layout at every destination: K / V of all ranks [P, Lr, W] == [L, W] (slot = sending rank), Q of the replica
-        [Pu, Lr, W] (slot = the sender's place in the replica), output [Lr, Pu * W] (column block = the head group the
-        sender computed) - exactly what the attention kernel and the output projection read, so nothing is repacked.
-        Two barriers per attention: operands landed / outputs landed.  The second one also orders this block's reads of
-        K, V, Q before the next block's stores into them (a rank only reaches it after its own attention kernel)."""
-        import b200q
-        P = self.world_size
-        es = q.element_size()
-        base, off, me = peer["base"], peer["off"], self.rank
-        slot = Lr * W * es
+    def _peer_messages_in(self, q, k, v, peer, Lr, W, Pu, g, h):
+        """(src, dst, src_pitch) of the operand exchange: my K / V columns of head group gp go to slot `my rank` of every
+        rank computing gp; my Q columns of head group gp go to slot `my place in the replica` of the ranks of my replica."""
+        P, es = self.world_size, q.element_size()
+        base, off, me, slot = peer["base"], peer["off"], self.rank, Lr * W * q.element_size()
         src, dst, pitch = [], [], []
         for dest in range(P):
             gp, hp = dest % Pu, dest // Pu                    # the destination computes head group gp for replica hp's queries
@@ -239,22 +225,58 @@ class SequenceParallel:
                 src.append(q.data_ptr() + col); dst.append(base[dest] + off["q"] + g * slot); pitch.append(q.stride(0) * es)
             if dest != me:
                 self.bytes_sent += (3 if hp == h else 2) * slot
+        return src, dst, pitch
+
+    def _peer_messages_out(self, O, peer, okey, Lr, W, Pu, g, h):
+        """(src, dst, src_pitch) of the output exchange: rows i*Lr.. of my result belong to rank h*Pu + i and land in column
+        block g (the head group I computed) of its [Lr, Pu*W] output buffer."""
+        es = O.element_size()
+        base, off, me = peer["base"], peer["off"], self.rank
+        src, dst, pitch = [], [], []
+        for i in range(Pu):
+            dest = h * Pu + i
+            src.append(O.data_ptr() + i * Lr * O.stride(0) * es); dst.append(base[dest] + off[okey] + g * W * es)
+            pitch.append(O.stride(0) * es)
+            if dest != me:
+                self.bytes_sent += Lr * W * es
+        return src, dst, pitch
+
+    def _attention_peer(self, q, k, v, core, peer, Lr, W, Pu, Pr, g, h, Hg):
+        """attention() with both exchanges as direct stores into the peers' buffers (include/b200q.h b200q_scatter_rows).
+        Layout at every destination: K / V of all ranks [P, Lr, W] == [L, W] (slot = sending rank), Q of the replica
+        [Pu, Lr, W] (slot = the sender's place in the replica), output [Lr, Pu * W] (column block = the head group the
+        sender computed) - exactly what the attention kernel and the output projection read, so nothing is repacked.
+        Two barriers per attention: operands landed / outputs landed.  The second one also orders this block's reads of
+        K, V, Q before the next block's stores into them (a rank only reaches it after its own attention kernel)."""
+        import b200q
+        es = q.element_size()
+        src, dst, pitch = self._peer_messages_in(q, k, v, peer, Lr, W, Pu, g, h)
         b200q.scatter_rows(src, dst, Lr, W * es, pitch, W * es)
         peer["hdl"].barrier()
         O = core(peer["Q"], peer["K"], peer["V"], Hg)              # [Pu * Lr, W]: my head group for the replica's queries
         which = self._peer_calls & 1                                # two output buffers: CFG branches are attended back to back
         self._peer_calls += 1
-        okey = "o1" if which else "o0"
-        src, dst, pitch = [], [], []
-        for i in range(Pu):                                         # rows i*Lr.. belong to rank h*Pu + i; I computed head group g
-            dest = h * Pu + i
-            src.append(O.data_ptr() + i * Lr * O.stride(0) * es); dst.append(base[dest] + off[okey] + g * W * es)
-            pitch.append(O.stride(0) * es)
-            if dest != me:
-                self.bytes_sent += slot
+        src, dst, pitch = self._peer_messages_out(O, peer, "o1" if which else "o0", Lr, W, Pu, g, h)
         b200q.scatter_rows(src, dst, Lr, W * es, pitch, Pu * W * es)
         peer["hdl"].barrier()
         return peer["O"][which]                                     # [Lr, H*hd]
+
+    @staticmethod
+    def peer_layout(buf, Lr, W, P, Pu):
+        """Views and byte offsets of one rank's exchange buffer: [K of all ranks | V of all ranks | Q of my replica | 2 x output]."""
+        n_k, n_q, n_o = P * Lr * W, Pu * Lr * W, Lr * Pu * W
+        es = buf.element_size()
+        off = {"k": 0, "v": n_k, "q": 2 * n_k, "o0": 2 * n_k + n_q, "o1": 2 * n_k + n_q + n_o}
+        return {
+            "buf": buf, "off": {k_: v_ * es for k_, v_ in off.items()},
+            "K": buf[off["k"]:off["k"] + n_k].view(P * Lr, W), "V": buf[off["v"]:off["v"] + n_k].view(P * Lr, W),
+            "Q": buf[off["q"]:off["q"] + n_q].view(Pu * Lr, W),
+            "O": [buf[off["o0"]:off["o0"] + n_o].view(Lr, Pu * W), buf[off["o1"]:off["o1"] + n_o].view(Lr, Pu * W)],
+        }
+
+    @staticmethod
+    def peer_numel(Lr, W, P, Pu):
+        return 2 * P * Lr * W + Pu * Lr * W + 2 * Lr * Pu * W
 
     def _attention_pipelined(self, q, k, v, core, Lr, hd, Pu, Pr, g, h, Hg, C):
         """Head-chunked variant of attention(): the heads of a group travel and are attended in C chunks.  Staging layout
