@@ -591,7 +591,7 @@ def run_b200(args):
             t_, o_, n_ = as_[dom_a]
             ach = o_ / (t_ * 1e-3) / 1e12
             own = attn != "library"
-            kern = {"b200q": "attn_bf16_kernel (tcgen05.mma.kind::f16, TMA, TMEM; this repo)", "int8": "attn_i8_kernel (tcgen05.mma.kind::i8; this repo)",
+            kern = {"b200q": "attn_bf16_kp_kernel (key-pipelined, tcgen05.mma.cta_group::2.kind::f16, TMA, TMEM; this repo)", "int8": "attn_i8_kernel (tcgen05.mma.kind::i8; this repo)",
                     "library": "torch SDPA (cuDNN flash attention; library, not this repo's code)"}[attn]
             # DRAM bytes per launch from the committed ncu --set full capture of the same kernel at the 1.3B self-attention
             # shape (profiles/traffic.json); other shapes have no capture -> null

@@ -37,6 +37,7 @@ from qdiff.base.quant_layer import ActPlan  # noqa: E402
 plan = ActPlan.rotation(D, torch.ones(D), torch.rand(D) + 0.5, dev)
 H = 12
 qb, kb, vb = (torch.randn(L, D, device=dev).to(torch.bfloat16) for _ in range(3))
+xdst = torch.empty(12 * (L // 4) * (D // 4), device=dev, dtype=torch.bfloat16)
 
 
 def one_pass():
@@ -53,6 +54,11 @@ def one_pass():
     b200q.gemm_w4a8(qa, w4, D, da, dwf, zf, rs, bf)
     b200q.gemm_w8a8(qa, w_qkv, da, dwq, zq, rs, bq)                                            # D->3D (q|k|v), bf16 out
     b200q.attn_bf16(qb, kb, vb, H)                                                             # attention core of configs[1]
+    # exchange data movement of a 4-rank step (local destinations here): q|k|v head-group slices of 8190 rows
+    Lr, Wg = L // 4, D // 4
+    b200q.scatter_rows([t.data_ptr() + gp * Wg * 2 for gp in range(4) for t in (kb, vb, qb)],
+                       [xdst.data_ptr() + i * Lr * Wg * 2 for i in range(12)], Lr, Wg * 2,
+                       [t.stride(0) * 2 for gp in range(4) for t in (kb, vb, qb)], Wg * 2)
     # quantized attention path (configs[4]): fused Q/K quantizer, V^T quantizer, int8 attention (H=12, L=32760)
     qq, dq, _ = b200q.rmsnorm_rope_quant(qkv[:, :D], dwd, 1e-6, cos, sin, 128)
     kq, dk, _ = b200q.rmsnorm_rope_quant(qkv[:, D:2 * D], dwd, 1e-6, cos, sin, 128)

@@ -64,7 +64,7 @@ if os.path.exists(rep) or os.path.exists(raw_csv):
     attn_rows = [r for r in rows[2:] if "attn_i8_kernel" in r[col["Kernel Name"]]]
     if attn_rows:
         traffic["attn_i8_H12_L32760"] = to_bytes(attn_rows[0], "dram__bytes_read.sum") + to_bytes(attn_rows[0], "dram__bytes_write.sum")
-    for key, pat in (("attn_bf16_H12_L32760", "attn_bf16_kernel"), ("ln_mod_quant_32760x1536", "ln_mod_quant_kernel"),
+    for key, pat in (("attn_bf16_H12_L32760", "attn_bf16_kp_kernel"), ("ln_mod_quant_32760x1536", "ln_mod_quant_kernel"),
                      ("rmsnorm_rope_32760x1536", "rmsnorm_rope_kernel"), ("had_quant_rows_32760x1536", "had_")):
         rr = [r for r in rows[2:] if pat in r[col["Kernel Name"]]]
         if rr:
