@@ -455,7 +455,7 @@ def run_b200(args):
     if world == 1:
         try:
             M.qlinear = wrapped("gemm", orig_qlinear, lambda qa, da, rs, w, *a, **kw: (qa.shape[0], w.N, w.K, 2.0 * qa.shape[0] * w.N * w.K))
-            M.attention_bf16 = wrapped("attn", orig_attn_bf16, lambda q, k, v, H: (q.shape[0], k.shape[0], q.shape[1], 4.0 * q.shape[0] * k.shape[0] * q.shape[1]))
+            M.attention_bf16 = wrapped("attn", orig_attn_bf16, lambda q, k, v, H, **kw: (q.shape[0], k.shape[0], q.shape[1], 4.0 * q.shape[0] * k.shape[0] * q.shape[1]))
             b200q.attn_i8 = wrapped("attn", orig_attn_i8, lambda qq, dq, kq, *a, **kw: (qq.shape[0], kq.shape[0], qq.shape[1], 4.0 * qq.shape[0] * kq.shape[0] * qq.shape[1]))
 
             class _Counted:

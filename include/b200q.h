@@ -198,6 +198,12 @@ B200Q_API int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int64
  * view (quant_opensora.py:430-435; base_quantizer.py:110-129,151-157).  q_out int8 [rows, cols] (ldq), dq_out fp32
  * [rows, cols/head_dim].  head_dim must be 128 (pass head_dim = 128 even without RoPE tables, e.g. cross-attention q/k).
  * `out` (bf16) may be NULL when only the codes are wanted. */
+/* b200q_rmsnorm_rope that also leaves, per 128-column head, the maximum over the rows of the squared norm of its bf16
+ * output in head_sq_max fp32 [cols / 128] (merged with atomicMax: the caller zeroes it; several calls may accumulate into
+ * it).  Input of b200q_attn_bf16_prenorm: the attention's bounded-head classification without another pass over q and k. */
+B200Q_API int b200q_rmsnorm_rope_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
+                             const float* weight, float eps, const float* cos_t, const float* sin_t, int head_dim,
+                             void* out, int64_t ldo, float* head_sq_max, b200q_stream_t stream);
 B200Q_API int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
                              const float* weight, float eps, const float* cos_t, const float* sin_t, int head_dim,
                              void* out, int64_t ldo, int8_t* q_out, int64_t ldq, float* dq_out, int n_bits,
@@ -256,6 +262,14 @@ B200Q_API int b200q_quant_vt(const void* v, int v_dtype, int64_t Lk, int64_t C, 
 B200Q_API int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                     int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
                     float* lse_out, int n_splits, void* part_ws, float* lse_ws, float* qk_norm_ws, b200q_stream_t stream);
+/* b200q_attn_bf16 with the head classification input precomputed: qk_sq_max fp32 [2, H] = per head, the maximum over the
+ * rows of |q_i|^2 (first H entries) and |k_j|^2 (next H) of the bf16 operands - what b200q_rmsnorm_rope_stats leaves behind -
+ * so the launch that re-reads q and k is skipped.  Values larger than the true maxima are safe (a head is then merely
+ * classified unbounded more often); inf / NaN classify the head as unbounded. */
+B200Q_API int b200q_attn_bf16_prenorm(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                            int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
+                            float* lse_out, int n_splits, void* part_ws, float* lse_ws, const float* qk_sq_max,
+                            b200q_stream_t stream);
 /* Key-split count b200q_attn_bf16 should be called with for this shape on the current device (1 = no split). */
 B200Q_API int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads);
 

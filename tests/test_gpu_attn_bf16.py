@@ -198,3 +198,37 @@ def test_attn_bf16_kernel_variants(dev, variant, cl, H, Lq, Lk):
     assert torch.equal(out, again)
     if split is not None:
         _check(split, ref)
+
+
+def test_rmsnorm_rope_head_norm_maxima_feed_the_attention_classification(dev):
+    """b200q_rmsnorm_rope_stats leaves max_i |q_i,h|^2 of its bf16 output per 128-wide head (accumulating over calls);
+    b200q_attn_bf16_prenorm classifies the heads from those instead of re-reading q and k: same kernels, same result.
+    A head pushed over the bound (huge key rows) must take the online-softmax kernel through this path too."""
+    H, L, Lk = 6, 777, 1300
+    D = H * 128
+    g = torch.Generator(device="cuda").manual_seed(11)
+    xq = torch.randn(L, 3 * D, device=dev, generator=g).to(torch.bfloat16)[:, :D]          # strided source, as in the block
+    xk = torch.randn(Lk, D, device=dev, generator=g).to(torch.bfloat16)
+    xk[5, 256:384] *= 60.0                                                                  # head 2: one dominant key row
+    v = torch.randn(Lk, D, device=dev, generator=g).to(torch.bfloat16)
+    wq, wk = torch.rand(D, device=dev, generator=g) + 0.5, (torch.rand(D, device=dev, generator=g) + 0.5) * 3.0
+    cos = torch.rand(L, 64, device=dev, generator=g); sin = torch.rand(L, 64, device=dev, generator=g)
+    nrm = torch.zeros(2 * H, device=dev)
+    q = b200q.rmsnorm_rope(xq, wq, 1e-6, cos, sin, 128, head_sq_max=nrm[:H])
+    k = b200q.rmsnorm_rope(xk, wk, 1e-6, None, None, 0, head_sq_max=nrm[H:])
+    assert torch.equal(q, b200q.rmsnorm_rope(xq, wq, 1e-6, cos, sin, 128))                  # the output itself is unchanged
+    want = torch.cat([q.float().view(L, H, 128).square().sum(-1).amax(0), k.float().view(Lk, H, 128).square().sum(-1).amax(0)])
+    assert torch.allclose(nrm, want, rtol=1e-5, atol=0)
+    half = nrm.clone()
+    b200q.rmsnorm_rope(xq[: L // 2], wq, 1e-6, cos[: L // 2], sin[: L // 2], 128, head_sq_max=half[:H])   # accumulates: max stays
+    assert torch.equal(half, nrm)
+    out_pre, lse_pre = b200q.attn_bf16(q, k, v, H, want_lse=True, qk_sq_max=nrm)
+    out, lse = b200q.attn_bf16(q, k, v, H, want_lse=True)
+    assert torch.equal(out_pre, out) and torch.equal(lse_pre, lse)
+    bound = (nrm[:H] * nrm[H:]).sqrt() * 128 ** -0.5 * 1.4426950408889634
+    assert (bound > 80).any() and (bound <= 80).any()                                        # both kernels were exercised
+    _check(out_pre, _ref(q, k, v, H)[0], tol=3e-2)
+    with pytest.raises(b200q.B200QError):
+        b200q.attn_bf16(q, k, v, H, qk_sq_max=nrm[:H])
+    with pytest.raises(b200q.B200QError):
+        b200q.rmsnorm_rope(xq, wq, 1e-6, cos, sin, 128, head_sq_max=nrm)

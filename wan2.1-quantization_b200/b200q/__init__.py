@@ -67,6 +67,10 @@ _SIGNATURES = {
     "b200q_attn_bf16_set_mode": (c_int, [c_int]),
     "b200q_attn_bf16": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
                                 c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200q_attn_bf16_prenorm": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64, c_int64, c_int, c_int, c_float,
+                                        c_void_p, c_int64, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "b200q_rmsnorm_rope_stats": (c_int, [c_void_p, c_int, c_int64, c_int64, c_int64, c_void_p, c_float, c_void_p, c_void_p, c_int,
+                                         c_void_p, c_int64, c_void_p, c_void_p]),
     "b200q_attn_bf16_set_fast": (c_int, [c_int]),
     "b200q_attn_bf16_set_cluster": (c_int, [c_int]),
     "b200q_attn_bf16_set_variant": (c_int, [c_int]),
@@ -359,14 +363,22 @@ def gate_residual(y, residual, gate=None, out=None):
     return out
 
 
-def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0):
+def rmsnorm_rope(x, weight, eps, cos=None, sin=None, head_dim=0, head_sq_max=None):
     """RMSNorm over the full dim (+ RoPE when cos/sin [rows, head_dim/2] are given); x bf16/fp16 [rows, cols] (may be a
-    strided column slice) -> bf16 [rows, cols]."""
+    strided column slice) -> bf16 [rows, cols].  head_sq_max (fp32 [cols/128], zeroed by the caller): also accumulate the
+    per-head maxima of the squared output row norms (the attention's bounded-head classification input)."""
     _cuda(x, "rmsnorm_rope")
     if x.dim() != 2 or x.stride(1) != 1:
         raise B200QError("rmsnorm_rope: expected a row-major 2-D tensor")
     rows, cols = x.shape
     out = torch.empty((rows, cols), dtype=torch.bfloat16, device=x.device)
+    if head_sq_max is not None:
+        if head_sq_max.dtype != torch.float32 or head_sq_max.numel() != cols // 128 or not head_sq_max.is_contiguous():
+            raise B200QError("rmsnorm_rope: head_sq_max must be a contiguous fp32 tensor of cols / 128 values")
+        rc = load().b200q_rmsnorm_rope_stats(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(weight), float(eps), _ptr(cos),
+                                             _ptr(sin), int(head_dim), _ptr(out), _ld(out), _ptr(head_sq_max), _stream())
+        _check(rc, "b200q_rmsnorm_rope_stats")
+        return out
     rc = load().b200q_rmsnorm_rope(_ptr(x), _DTYPE[x.dtype], rows, cols, _ld(x), _ptr(weight), float(eps), _ptr(cos),
                                    _ptr(sin), int(head_dim), _ptr(out), _ld(out), _stream())
     _check(rc, "b200q_rmsnorm_rope")
@@ -416,10 +428,12 @@ attn_bf16_default_splits = None
 attn_bf16_bounded_heads = True      # classify heads by the Cauchy-Schwarz score bound and run bounded heads max-free
 
 
-def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_splits=None):
+def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_splits=None, qk_sq_max=None):
     """bf16 flash attention (include/b200q.h): q [Lq, H*128], k, v [Lk, H*128] bf16 (row-major, any row pitch that is a
     multiple of 8 elements) -> bf16 [Lq, H*128]; want_lse=True also returns the fp32 [H, Lq] log2-sum-exp.
-    n_splits: key splits per work item (None = the library's proposal for this shape; 1 = none)."""
+    n_splits: key splits per work item (None = the library's proposal for this shape; 1 = none).
+    qk_sq_max: fp32 [2*H] per-head maxima of |q_i|^2, |k_j|^2 left behind by rmsnorm_rope(head_sq_max=...): skips the
+    pre-pass over q and k (b200q_attn_bf16_prenorm)."""
     for t, n in ((q, "q"), (k, "k"), (v, "v")):
         _cuda(t, n)
         if t.dtype != torch.bfloat16 or t.dim() != 2 or t.stride(1) != 1:
@@ -442,6 +456,13 @@ def attn_bf16(q, k, v, num_heads, sm_scale=None, out=None, want_lse=False, n_spl
     if n_splits > 1:
         part = torch.empty((n_splits, Lq, D), dtype=torch.bfloat16, device=q.device)
         lse_ws = torch.empty((n_splits, H, Lq), dtype=torch.float32, device=q.device)
+    if qk_sq_max is not None and attn_bf16_bounded_heads:
+        if qk_sq_max.dtype != torch.float32 or qk_sq_max.numel() != 2 * H or not qk_sq_max.is_contiguous():
+            raise B200QError("attn_bf16: qk_sq_max must be a contiguous fp32 tensor of 2 * heads values")
+        rc = load().b200q_attn_bf16_prenorm(_ptr(q), _ld(q), _ptr(k), _ld(k), _ptr(v), _ld(v), Lq, Lk, H, hd, sm_scale, _ptr(out),
+                                            _ld(out), _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _ptr(qk_sq_max), _stream())
+        _check(rc, "b200q_attn_bf16_prenorm")
+        return (out, lse) if want_lse else out
     rc = load().b200q_attn_bf16(_ptr(q), _ld(q), _ptr(k), _ld(k), _ptr(v), _ld(v), Lq, Lk, H, hd, sm_scale, _ptr(out), _ld(out),
                                 _ptr(lse), int(n_splits), _ptr(part), _ptr(lse_ws), _ptr(norm_ws), _stream())
     _check(rc, "b200q_attn_bf16")

@@ -1245,10 +1245,31 @@ static int launch_fa_any(bool fast, int poly, int cl, const CUtensorMap& tq, con
   return fast ? launch_fa_poly<true, 1>(poly, tq, tk, tv, p, st) : launch_fa_poly<false, 1>(poly, tq, tk, tv, p, st);
 }
 
+static int attn_bf16_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t Lq, int64_t Lk,
+                          int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo, float* lse_out, int n_splits,
+                          void* part_ws, float* lse_ws, float* qk_norm_ws, bool norms_given, b200q_stream_t stream);
+
 extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
                                int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
                                float* lse_out, int n_splits, void* part_ws, float* lse_ws, float* qk_norm_ws,
                                b200q_stream_t stream) {
+  return attn_bf16_impl(q, ldq, k, ldk, v, ldv, Lq, Lk, num_heads, head_dim, sm_scale, out, ldo, lse_out, n_splits, part_ws, lse_ws,
+                        qk_norm_ws, false, stream);
+}
+
+extern "C" int b200q_attn_bf16_prenorm(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv,
+                                       int64_t Lq, int64_t Lk, int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo,
+                                       float* lse_out, int n_splits, void* part_ws, float* lse_ws, const float* qk_sq_max,
+                                       b200q_stream_t stream) {
+  clear_error();
+  B200Q_REQUIRE(qk_sq_max != nullptr, B200Q_ERR_BAD_ARG, "attn_bf16_prenorm: qk_sq_max [2, heads] required");
+  return attn_bf16_impl(q, ldq, k, ldk, v, ldv, Lq, Lk, num_heads, head_dim, sm_scale, out, ldo, lse_out, n_splits, part_ws, lse_ws,
+                        const_cast<float*>(qk_sq_max), true, stream);
+}
+
+static int attn_bf16_impl(const void* q, int64_t ldq, const void* k, int64_t ldk, const void* v, int64_t ldv, int64_t Lq, int64_t Lk,
+                          int num_heads, int head_dim, float sm_scale, void* out, int64_t ldo, float* lse_out, int n_splits,
+                          void* part_ws, float* lse_ws, float* qk_norm_ws, bool norms_given, b200q_stream_t stream) {
   clear_error();
   using namespace fa;
   B200Q_REQUIRE(q && k && v && out, B200Q_ERR_BAD_ARG, "attn_bf16: null pointer");
@@ -1291,10 +1312,12 @@ extern "C" int b200q_attn_bf16(const void* q, int64_t ldq, const void* k, int64_
   if (p.qk_norm != nullptr) {
     // classify the heads (bounded scores -> max-free kernel), then run both kernels over the item list: each skips the
     // other's heads, so a launch whose class is empty costs a few microseconds
-    B200Q_CUDA_OK(cudaMemsetAsync(qk_norm_ws, 0, sizeof(float) * 2 * num_heads, st));
-    attn_qk_norm_kernel<<<dim3(64, 2 * num_heads), 256, 0, st>>>((const __nv_bfloat16*)q, ldq, (int)Lq, (const __nv_bfloat16*)k, ldk,
-                                                                 (int)Lk, num_heads, qk_norm_ws);
-    B200Q_CHECK_LAUNCH();
+    if (!norms_given) {
+      B200Q_CUDA_OK(cudaMemsetAsync(qk_norm_ws, 0, sizeof(float) * 2 * num_heads, st));
+      attn_qk_norm_kernel<<<dim3(64, 2 * num_heads), 256, 0, st>>>((const __nv_bfloat16*)q, ldq, (int)Lq, (const __nv_bfloat16*)k, ldk,
+                                                                   (int)Lk, num_heads, qk_norm_ws);
+      B200Q_CHECK_LAUNCH();
+    }
     if (g_fa_kp) {
       // bounded heads on the key-pipelined kernel: 256-query items on CTA pairs, K boxes of 64 keys
       Params pq = p;

@@ -261,6 +261,10 @@ struct RopeArgs {
   int64_t ldq;
   float* dq_out;
   float n_levels;
+  // optional: per 128-column head, the maximum over the rows of the squared norm of the bf16 OUTPUT (what the attention
+  // kernel will read): head_sq_max[cols / 128], merged with atomicMax (the caller zeroes it).  b200q_attn_bf16_prenorm
+  // classifies bounded heads from these instead of re-reading q and k in a pre-pass.
+  float* head_sq_max;
 };
 
 template <typename T, int V, int THREADS>
@@ -268,6 +272,11 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
   using VT = Vec16<T>;
   constexpr int N = VT::N;            // 8 (bf16 / fp16)
   __shared__ float s_buf[32];
+  __shared__ int s_hmax[64];          // per-head maxima of this CTA's rows (bit patterns of non-negative floats)
+  if (a.head_sq_max != nullptr) {
+    if (threadIdx.x < 64) s_hmax[threadIdx.x] = 0;
+    __syncthreads();
+  }
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rows_per_cta = (THREADS / 32) / warps_per_row;
   const int row_in_cta = warp / warps_per_row;
@@ -334,6 +343,20 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
       stg_stream16(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + c0, *reinterpret_cast<uint4*>(o));
+      if (a.head_sq_max != nullptr) {
+        // a 128-column head = 16 consecutive lanes (cols is a multiple of 128, so every lane of the group is live)
+        float ss2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float2 f2 = __bfloat1622float2(o[i]);
+          ss2 = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, ss2));
+        }
+        const unsigned grp = 0xffffu << (lane & 16);
+#pragma unroll
+        for (int sh = 8; sh > 0; sh >>= 1) ss2 += __shfl_xor_sync(grp, ss2, sh);
+        if (ss2 != ss2) ss2 = INFINITY;                          // NaN row: the head is unbounded
+        if ((lane & 15) == 0) atomicMax(&s_hmax[c0 >> 7], __float_as_int(ss2));
+      }
     }
     if (a.q_out != nullptr) {
       // a head (head_dim == 128 == 16 vectors) is held by 16 consecutive lanes: |y| max by 4 shuffles.  Every lane of
@@ -356,6 +379,16 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
       }
       stg_stream8(a.q_out + row * a.ldq + c0, make_uint2(w[0], w[1]));
       if ((lane & 15) == 0) a.dq_out[row * (a.cols / a.head_dim) + c0 / a.head_dim] = d;
+    }
+  }
+  if (a.head_sq_max != nullptr) {
+    __syncthreads();
+    // thousands of CTAs, a dozen addresses: an atomic per CTA and head would serialise in L2 (measured: +12 us per launch).
+    // The maximum only grows, so a CTA that does not exceed the value it reads (L2, uncached in L1) has nothing to add.
+    if (threadIdx.x < (int)(a.cols >> 7)) {
+      int* dst = reinterpret_cast<int*>(a.head_sq_max) + threadIdx.x;
+      const int mine = s_hmax[threadIdx.x];
+      if (mine > __ldcg(dst)) atomicMax(dst, mine);
     }
   }
 }
@@ -515,10 +548,31 @@ extern "C" int b200q_rmsnorm_rope(const void* x, int x_dtype, int64_t rows, int6
                                   nullptr, 8, stream);
 }
 
+static int rmsnorm_rope_impl(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, const float* weight, float eps,
+                             const float* cos_t, const float* sin_t, int head_dim, void* out, int64_t ldo, int8_t* q_out,
+                             int64_t ldq, float* dq_out, int n_bits, float* head_sq_max, b200q_stream_t stream);
+
 extern "C" int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx,
                                         const float* weight, float eps, const float* cos_t, const float* sin_t,
                                         int head_dim, void* out, int64_t ldo, int8_t* q_out, int64_t ldq, float* dq_out,
                                         int n_bits, b200q_stream_t stream) {
+  return rmsnorm_rope_impl(x, x_dtype, rows, cols, ldx, weight, eps, cos_t, sin_t, head_dim, out, ldo, q_out, ldq, dq_out, n_bits,
+                           nullptr, stream);
+}
+
+extern "C" int b200q_rmsnorm_rope_stats(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, const float* weight,
+                                        float eps, const float* cos_t, const float* sin_t, int head_dim, void* out, int64_t ldo,
+                                        float* head_sq_max, b200q_stream_t stream) {
+  B200Q_REQUIRE(out != nullptr || rows == 0 || cols == 0, B200Q_ERR_BAD_ARG, "rmsnorm_rope_stats: null pointer");
+  B200Q_REQUIRE(head_sq_max != nullptr && cols % 128 == 0 && cols <= 64 * 128, B200Q_ERR_BAD_ARG,
+                "rmsnorm_rope_stats: head_sq_max [cols / 128] required, cols a multiple of 128 (at most 64 heads)");
+  return rmsnorm_rope_impl(x, x_dtype, rows, cols, ldx, weight, eps, cos_t, sin_t, head_dim, out, ldo, nullptr, 0, nullptr, 8,
+                           head_sq_max, stream);
+}
+
+static int rmsnorm_rope_impl(const void* x, int x_dtype, int64_t rows, int64_t cols, int64_t ldx, const float* weight, float eps,
+                             const float* cos_t, const float* sin_t, int head_dim, void* out, int64_t ldo, int8_t* q_out,
+                             int64_t ldq, float* dq_out, int n_bits, float* head_sq_max, b200q_stream_t stream) {
   clear_error();
   B200Q_REQUIRE(rows >= 0 && cols >= 0, B200Q_ERR_BAD_ARG, "rmsnorm_rope: negative shape");
   if (rows == 0 || cols == 0) return B200Q_OK;
@@ -544,6 +598,7 @@ extern "C" int b200q_rmsnorm_rope_quant(const void* x, int x_dtype, int64_t rows
   a.x = x; a.rows = rows; a.cols = cols; a.ldx = ldx; a.weight = weight; a.eps = eps; a.cos_t = cos_t; a.sin_t = sin_t;
   a.head_dim = head_dim > 0 ? head_dim : (int)cols; a.out = out; a.ldo = ldo;
   a.q_out = q_out; a.ldq = ldq; a.dq_out = dq_out; a.n_levels = (float)((1 << (n_bits - 1)) - 1);
+  a.head_sq_max = head_sq_max;
   if (x_dtype == B200Q_BF16) return launch_rope<__nv_bfloat16>(a, (cudaStream_t)stream);
   return launch_rope<__half>(a, (cudaStream_t)stream);
 }

@@ -250,10 +250,11 @@ def _rope_table(head_dim, grid, device, pos_offset=0, length=None):
     return a.cos().float().to(device).contiguous(), a.sin().float().to(device).contiguous()
 
 
-def rmsnorm_rope(x, weight, eps, cos=None, sin=None, num_heads=1):
+def rmsnorm_rope(x, weight, eps, cos=None, sin=None, num_heads=1, head_sq_max=None):
     """WanRMSNorm over the FULL model dim (model.py:73-89, 127-128) then optional RoPE on [L, H, hd] pairs: one fused
-    kernel.  x bf16 [L, D] (may be a strided column slice of the fused qkv output) -> bf16 [L, D] contiguous."""
-    return b200q.rmsnorm_rope(x, weight, eps, cos, sin, x.shape[1] // num_heads)
+    kernel.  x bf16 [L, D] (may be a strided column slice of the fused qkv output) -> bf16 [L, D] contiguous.
+    head_sq_max: see b200q.rmsnorm_rope (per-head maxima of the squared output row norms for the attention core)."""
+    return b200q.rmsnorm_rope(x, weight, eps, cos, sin, x.shape[1] // num_heads, head_sq_max=head_sq_max)
 
 
 def attention_i8(q, k, v, num_heads):
@@ -294,11 +295,18 @@ def set_attention_core(name):
     ATTENTION_CORE = name
 
 
-def attention_bf16(q, k, v, num_heads):
-    """bf16 attention core, q [Lq, H*hd], k,v [Lk, H*hd] (any row pitch) -> [Lq, H*hd] bf16."""
+def attention_bf16(q, k, v, num_heads, qk_sq_max=None):
+    """bf16 attention core, q [Lq, H*hd], k,v [Lk, H*hd] (any row pitch) -> [Lq, H*hd] bf16.  qk_sq_max: per-head maxima of
+    the squared q / k row norms when the producing RMSNorm+RoPE kernels already took them (own kernel only)."""
     if ATTENTION_CORE == "b200q":
-        return b200q.attn_bf16(q, k, v, num_heads)
+        return b200q.attn_bf16(q, k, v, num_heads, qk_sq_max=qk_sq_max)
     return sdpa(q, k, v, num_heads)
+
+
+def fused_head_norms(cfg):
+    """True when the RMSNorm+RoPE kernels should leave the per-head norm maxima for the attention core (own bf16 kernel,
+    128-wide heads): saves the core's pre-pass over q and k."""
+    return ATTENTION_CORE == "b200q" and cfg.head_dim == 128 and cfg.num_heads <= 64 and b200q.attn_bf16_bounded_heads
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -381,8 +389,8 @@ class WanBlockQ:
         return WanBlockQ(cfg, w, attn_quant=attn_quant)
 
     # ---- building blocks ----------------------------------------------------------------------------------
-    def _default_attention(self, q, k, v):
-        return attention_bf16(q, k, v, self.cfg.num_heads)
+    def _default_attention(self, q, k, v, qk_sq_max=None):
+        return attention_bf16(q, k, v, self.cfg.num_heads, qk_sq_max=qk_sq_max)
 
     def _ln_act(self, x, consumers, **ln):
         """LayerNorm (+ affine / adaLN modulate) of the fp32 residual stream, emitted in the forms `consumers` need:
@@ -410,11 +418,11 @@ class WanBlockQ:
     def _group(self, fused, names):
         return [fused] if fused is not None else [self.lin[n] for n in names]
 
-    def context_kv(self, context):
+    def context_kv(self, context, head_sq_max=None):
         """cross-attention K,V of the (rank-replicated) text context [T, D] — token-local, once per block."""
         cfg = self.cfg
         kv = self._project(Act(fp=context, a_bits=self.a_bits), self.w_ckv, ("cross_attn.k", "cross_attn.v"))   # [T, 2D] bf16
-        k = rmsnorm_rope(kv[:, :cfg.dim], self.cnorm_k, cfg.eps)
+        k = rmsnorm_rope(kv[:, :cfg.dim], self.cnorm_k, cfg.eps, head_sq_max=head_sq_max)
         return k, kv[:, cfg.dim:]
 
     def context_kv_i8(self, context):
@@ -456,11 +464,15 @@ class WanBlockQ:
                                   out=None if a is None else rows(a, b, L))
                 a = o if a is None else a
         else:
-            q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H)
-            k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H)
+            # own attention core without an exchange in the way: the RMSNorm+RoPE kernels leave the per-head norm maxima the
+            # core classifies its heads by (one bound over all CFG branches), so it does not re-read q and k
+            nrm = torch.zeros(2 * H, dtype=torch.float32, device=x.device) if (local_attention and fused_head_norms(cfg)) else None
+            kw = {} if nrm is None else {"qk_sq_max": nrm}
+            q = rmsnorm_rope(qkv[:, :D], self.norm_q, cfg.eps, cos, sin, H, head_sq_max=None if nrm is None else nrm[:H])
+            k = rmsnorm_rope(qkv[:, D:2 * D], self.norm_k, cfg.eps, cos, sin, H, head_sq_max=None if nrm is None else nrm[H:])
             v = qkv[:, 2 * D:]
-            a = attention(q, k, v) if B == 1 else torch.cat([attention(rows(q, b, L), rows(k, b, L), rows(v, b, L))
-                                                             for b in range(B)], 0)
+            a = attention(q, k, v, **kw) if B == 1 else torch.cat(
+                [attention(rows(q, b, L), rows(k, b, L), rows(v, b, L), **kw) for b in range(B)], 0)
         apply_linear(self.w_o, Act(fp=a, a_bits=self.a_bits), epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=e[2])
 
         # ---- cross attention (model.py:180-200, 351-353) ----
@@ -474,10 +486,11 @@ class WanBlockQ:
                                   out=None if a is None else rows(a, b, L))
                 a = o if a is None else a
         else:
-            q = rmsnorm_rope(cq, self.cnorm_q, cfg.eps)
-            ck, cv = self.context_kv(context)
-            a = attention_bf16(q, ck, cv, H) if B == 1 else torch.cat(
-                [attention_bf16(rows(q, b, L), rows(ck, b, T), rows(cv, b, T), H) for b in range(B)], 0)
+            nrm = torch.zeros(2 * H, dtype=torch.float32, device=x.device) if fused_head_norms(cfg) else None
+            q = rmsnorm_rope(cq, self.cnorm_q, cfg.eps, head_sq_max=None if nrm is None else nrm[:H])
+            ck, cv = self.context_kv(context, head_sq_max=None if nrm is None else nrm[H:])
+            a = attention_bf16(q, ck, cv, H, qk_sq_max=nrm) if B == 1 else torch.cat(
+                [attention_bf16(rows(q, b, L), rows(ck, b, T), rows(cv, b, T), H, qk_sq_max=nrm) for b in range(B)], 0)
         apply_linear(self.w_co, Act(fp=a, a_bits=self.a_bits), epilogue=b200q.EPI_GATE_RESIDUAL, residual=x, gate=None)
 
         # ---- ffn (model.py:286-288, 359-362) ----
