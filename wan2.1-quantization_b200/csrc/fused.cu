@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
   const float ms = row_reduce_sum(ss, s_buf, warp, lane, w0, warps_per_row) / (float)a.cols;
   const float rstd = __frsqrt_rn(ms + a.eps);
   const int half = a.head_dim >> 1;
+  float hss[V];                                                  // head_sq_max only (dead code otherwise)
+#pragma unroll
+  for (int v = 0; v < V; ++v) hss[v] = 0.f;
 #pragma unroll
   for (int v = 0; v < V; ++v) {
     const int j = v * tpr + t;
@@ -343,19 +346,14 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
 #pragma unroll
       for (int i = 0; i < 4; ++i) o[i] = __floats2bfloat162_rn(y[2 * i], y[2 * i + 1]);
       stg_stream16(reinterpret_cast<__nv_bfloat16*>(a.out) + row * a.ldo + c0, *reinterpret_cast<uint4*>(o));
-      if (a.head_sq_max != nullptr) {
-        // a 128-column head = 16 consecutive lanes (cols is a multiple of 128, so every lane of the group is live)
+      if (a.head_sq_max != nullptr) {                            // this thread's share of |row, head|^2; reduced after the loop
         float ss2 = 0.f;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const float2 f2 = __bfloat1622float2(o[i]);
           ss2 = fmaf(f2.x, f2.x, fmaf(f2.y, f2.y, ss2));
         }
-        const unsigned grp = 0xffffu << (lane & 16);
-#pragma unroll
-        for (int sh = 8; sh > 0; sh >>= 1) ss2 += __shfl_xor_sync(grp, ss2, sh);
-        if (ss2 != ss2) ss2 = INFINITY;                          // NaN row: the head is unbounded
-        if ((lane & 15) == 0) atomicMax(&s_hmax[c0 >> 7], __float_as_int(ss2));
+        hss[v] = ss2;
       }
     }
     if (a.q_out != nullptr) {
@@ -382,6 +380,24 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
     }
   }
   if (a.head_sq_max != nullptr) {
+    // a 128-column head = 16 consecutive lanes of one vector slot (cols is a multiple of 128, so every lane of a live group
+    // is live): the V slots' shuffle trees run side by side instead of one dependent chain per slot inside the loop
+    if (row_ok) {
+#pragma unroll
+      for (int sh = 8; sh > 0; sh >>= 1) {
+#pragma unroll
+        for (int v = 0; v < V; ++v) hss[v] += __shfl_xor_sync(0xffffffffu, hss[v], sh);
+      }
+#pragma unroll
+      for (int v = 0; v < V; ++v) {
+        const int j = v * tpr + t;
+        if (j < kv && (lane & 15) == 0) {
+          float m = hss[v];
+          if (m != m) m = INFINITY;                              // NaN row: the head is unbounded
+          atomicMax(&s_hmax[(j * N) >> 7], __float_as_int(m));
+        }
+      }
+    }
     __syncthreads();
     // thousands of CTAs, a dozen addresses: an atomic per CTA and head would serialise in L2 (measured: +12 us per launch).
     // The maximum only grows, so a CTA that does not exceed the value it reads (L2, uncached in L1) has nothing to add.
