@@ -91,6 +91,13 @@ __device__ __forceinline__ bool head_is_bounded(const Params& p, int h) {
   const float b = sqrtf(p.qk_norm[h] * p.qk_norm[p.H + h]) * fabsf(p.scale_log2e);   // qk_norm holds squared norms
   return b <= FAST_BOUND;                                                 // false for NaN / inf
 }
+// No head of the wanted class in this launch (the usual case for one of the two kernels): every thread of every CTA sees
+// the same answer, so the kernel can return before it touches barriers, tensor memory or the cluster.
+__device__ __forceinline__ bool no_head_of_class(const Params& p, bool bounded) {
+  for (int h = 0; h < p.H; ++h)
+    if (head_is_bounded(p, h) == bounded) return false;
+  return true;
+}
 
 // kind::f16 instruction descriptor: D = fp32, A = B = bf16, A K-major; B K-major (Q.K^T) or MN-major (P.V)
 __host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, bool b_mn_major) {
@@ -348,6 +355,7 @@ attn_bf16_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_constant
   using Smem = SmemT<CL>;
   constexpr int KS = Smem::ks, VS = Smem::vs;
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (no_head_of_class(p, FAST)) return;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
     __trap();
@@ -782,6 +790,7 @@ attn_bf16_kp_kernel(const __grid_constant__ CUtensorMap tm_q, const __grid_const
   using Smem = SmemKP;
   constexpr int KS = Smem::ks, VS = Smem::vs;
   extern __shared__ __align__(1024) uint8_t smem[];
+  if (no_head_of_class(p, true)) return;
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("b200q: dynamic smem base not 1024-byte aligned\n");
     __trap();

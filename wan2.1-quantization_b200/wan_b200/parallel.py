@@ -133,6 +133,8 @@ class SequenceParallel:
         Pu, Pr, g, h = self.plan(num_heads)
         Hg = num_heads // Pu
         W = Hg * hd
+        if self.exchange == "peer" and not q.is_cuda:
+            raise RuntimeError("SequenceParallel(exchange='peer'): the peer-memory exchange needs CUDA tensors")
         if self.exchange != "nccl" and q.is_cuda:
             peer = self._peer_buffers(Lr, W, P, Pu, q.dtype, q.device)
             if peer is not None:
