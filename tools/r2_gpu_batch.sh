@@ -6,6 +6,8 @@ cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
 TAG=${TAG:-r2}
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/${TAG}_pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/${TAG}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" > gpurun_out/${TAG}_smoke.log 2>&1; echo "smoke rc=$?"; tail -1 gpurun_out/${TAG}_smoke.log
+timeout 120 python tools/probe_rope.py > gpurun_out/${TAG}_probe_rope.log 2>&1; cat gpurun_out/${TAG}_probe_rope.log
 timeout 600 python bench.py --steps 5 --warmup 3 > gpurun_out/${TAG}_bench.json 2> gpurun_out/${TAG}_bench.err; echo "bench rc=$?"
 timeout 600 python tools/run_kernels.py > gpurun_out/${TAG}_run_kernels.log 2>&1; echo "run_kernels rc=$?"
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2000 --csv --log-file gpurun_out/launches_${TAG}.csv \

@@ -301,6 +301,7 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
   const float ms = row_reduce_sum(ss, s_buf, warp, lane, w0, warps_per_row) / (float)a.cols;
   const float rstd = __frsqrt_rn(ms + a.eps);
   const int half = a.head_dim >> 1;
+  const bool hd_pow2 = (a.head_dim & (a.head_dim - 1)) == 0;
   float hss[V];                                                  // head_sq_max only (dead code otherwise)
 #pragma unroll
   for (int v = 0; v < V; ++v) hss[v] = 0.f;
@@ -330,7 +331,9 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
       }
     }
     if (a.cos_t != nullptr) {
-      const int p0 = (c0 % a.head_dim) >> 1;                 // first pair index inside the head (multiple of 4)
+      // first pair index inside the head (multiple of 4); head_dim is a power of two for every Wan model - a runtime
+      // integer modulo costs ~25 instructions per vector here
+      const int p0 = (hd_pow2 ? (c0 & (a.head_dim - 1)) : (c0 % a.head_dim)) >> 1;
       const float4 c4 = __ldg(reinterpret_cast<const float4*>(a.cos_t + row * half + p0));
       const float4 s4 = __ldg(reinterpret_cast<const float4*>(a.sin_t + row * half + p0));
       const float cv[4] = {c4.x, c4.y, c4.z, c4.w}, sv[4] = {s4.x, s4.y, s4.z, s4.w};
@@ -376,7 +379,7 @@ __global__ void __launch_bounds__(THREADS) rmsnorm_rope_kernel(const RopeArgs a,
         w[i >> 2] |= ((uint32_t)qv & 0xffu) << (8 * (i & 3));
       }
       stg_stream8(a.q_out + row * a.ldq + c0, make_uint2(w[0], w[1]));
-      if ((lane & 15) == 0) a.dq_out[row * (a.cols / a.head_dim) + c0 / a.head_dim] = d;
+      if ((lane & 15) == 0) a.dq_out[row * (a.cols >> 7) + (c0 >> 7)] = d;      // head_dim == 128 on this path
     }
   }
   if (a.head_sq_max != nullptr) {
