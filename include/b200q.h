@@ -224,8 +224,9 @@ B200Q_API int b200q_had_quant_rows(const void* x, int x_dtype, int64_t rows, int
                          const float* colscale, const float* hadK, int K, int log2_width, int n_bits,
                          int8_t* q, int64_t ldq, float* delta, int32_t* rowsum, float* y_out, int64_t ldy,
                          b200q_stream_t stream);
-/* Debug / benchmarking knob: 1 (default) = n = K*128 rows take the register-resident warp-per-row kernel, 0 = always the
- * shared-memory tile kernel.  Same function; the two differ in fp32 rounding order only. */
+/* Debug / benchmarking knob: 1 (default) = rows of n = K*128 (K = 8, 12) and n = 20*256 channels take the register-resident
+ * kernels (one / two warps per row), 0 = always the shared-memory tile kernel, 2 = like 1 with the three-CTAs-per-SM build
+ * of the two-warp kernel (slower: it spills).  Same function; the kernels differ in fp32 rounding order only. */
 B200Q_API int b200q_had_set_mode(int warp_kernel);
 
 /* ---- (c) quantized attention ------------------------------------------------------------

@@ -149,9 +149,11 @@ def test_variant_layer_fused_vs_reference_formula_gpu(dev, kind, n):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("n,dtype", [(1536, torch.float32), (1536, torch.bfloat16), (1024, torch.float16)])
+@pytest.mark.parametrize("n,dtype", [(1536, torch.float32), (1536, torch.bfloat16), (1024, torch.float16), (5120, torch.float32),
+                                     (5120, torch.bfloat16)])
 def test_had_quant_warp_kernel_vs_tile_kernel_gpu(dev, n, dtype):
-    """n = K*128 rows take the register-resident warp-per-row kernel (csrc/hadamard.cu); the shared-memory tile kernel stays
+    """n = K*128 rows take the register-resident warp-per-row kernel, n = 20*256 (the 14B hidden size) its two-warps-per-row
+    sibling (csrc/hadamard.cu); the shared-memory tile kernel stays
     selectable: same function, fp32 rounding order differs (base block before / after the Walsh-Hadamard stages)."""
     import b200q
     from qdiff.base.quant_layer import ActPlan

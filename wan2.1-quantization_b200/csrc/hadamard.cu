@@ -32,6 +32,7 @@ struct HadArgs {
 };
 
 constexpr int HAD_THREADS = 256;
+__device__ __forceinline__ void named_bar_sync_64(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 constexpr int HAD_KMAX = 32;
 
 // natural-order FWHT of one 32*E-wide segment held as E consecutive values per lane
@@ -378,6 +379,168 @@ static int launch_had_warp(const HadArgs& a, cudaStream_t st) {
   return B200Q_OK;
 }
 
+// ---- register-resident variant for n = K * 256 channels (Wan-14B hidden: 5120 = 20 * 256): TWO warps own one row ---------
+// Thread (w, l) holds positions w*128 + 4l .. + 3 of every one of the K segments.  Base block and the first seven
+// Walsh-Hadamard stages are those of the one-warp kernel; the eighth stage pairs the two warps through shared memory
+// (one float4 per segment and thread, [segment][thread] so that a warp's accesses are conflict-free); the row abs-max and
+// the code row sum meet through two shared words.  One HBM read, one HBM write.
+template <typename T, int K, int MINB>
+__global__ void __launch_bounds__(128, MINB) had_quant_warp2_kernel(const HadArgs a) {
+  __shared__ __align__(16) float s_h[K * K];
+  __shared__ float4 s_x[2][K][64];                  // [row of the CTA][segment][thread of the row]
+  __shared__ float s_m[2][2];
+  __shared__ int s_s[2][2];
+  for (int i = threadIdx.x; i < K * K; i += 128) s_h[i] = a.hadK[i];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int r = warp >> 1, w = warp & 1;            // row of the CTA, half of the row
+  const int t = w * 32 + lane;
+  const int64_t row = (int64_t)blockIdx.x * 2 + r;
+  if (row >= a.rows) return;                         // both warps of a row leave together
+  const int pos = w * 128 + lane * 4;
+  const T* xrow = reinterpret_cast<const T*>(a.x) + row * a.ldx + pos;
+
+  uint64_t v01[K], v23[K];
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float f0, f1, f2, f3;
+    if constexpr (sizeof(T) == 4) {
+      const uint4 q = ldg_stream16(xrow + s * 256);
+      f0 = __uint_as_float(q.x); f1 = __uint_as_float(q.y); f2 = __uint_as_float(q.z); f3 = __uint_as_float(q.w);
+    } else {
+      const uint2 q = *reinterpret_cast<const uint2*>(xrow + s * 256);
+      if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+        f0 = __uint_as_float(q.x << 16); f1 = __uint_as_float(q.x & 0xffff0000u);
+        f2 = __uint_as_float(q.y << 16); f3 = __uint_as_float(q.y & 0xffff0000u);
+      } else {
+        const float2 a2 = __half22float2(*reinterpret_cast<const __half2*>(&q.x)), b2 = __half22float2(*reinterpret_cast<const __half2*>(&q.y));
+        f0 = a2.x; f1 = a2.y; f2 = b2.x; f3 = b2.y;
+      }
+    }
+    v01[s] = pack_f32x2(f0, f1); v23[s] = pack_f32x2(f2, f3);
+    if (a.colscale != nullptr) {
+      const float4 c = __ldg(reinterpret_cast<const float4*>(a.colscale + s * 256 + pos));
+      v01[s] = mul_f32x2(v01[s], pack_f32x2(c.x, c.y));
+      v23[s] = mul_f32x2(v23[s], pack_f32x2(c.z, c.w));
+    }
+  }
+
+  // ---- order-K base block across the segments (lane-local), one position pair at a time ----
+  {
+    uint64_t o[K];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      uint64_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) { const float h = s_h[i * K + j]; acc = fma_f32x2(pack_f32x2(h, h), v01[j], acc); }
+      o[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) v01[i] = o[i];
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+      uint64_t acc = 0;
+#pragma unroll
+      for (int j = 0; j < K; ++j) { const float h = s_h[i * K + j]; acc = fma_f32x2(pack_f32x2(h, h), v23[j], acc); }
+      o[i] = acc;
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) v23[i] = o[i];
+  }
+
+  // ---- 256-point FWHT of every segment: 2 in-lane stages, 5 shuffle stages, 1 stage across the two warps ----
+  const uint64_t pm = pack_f32x2(1.f, -1.f);
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float a0, a1, a2, a3;
+    unpack_f32x2(v01[s], a0, a1); unpack_f32x2(v23[s], a2, a3);
+    const uint64_t p = fma_f32x2(pack_f32x2(a1, a1), pm, pack_f32x2(a0, a0));      // (a0 + a1, a0 - a1)
+    const uint64_t q = fma_f32x2(pack_f32x2(a3, a3), pm, pack_f32x2(a2, a2));      // (a2 + a3, a2 - a3)
+    v01[s] = add_f32x2(p, q);
+    v23[s] = fma_f32x2(q, pack_f32x2(-1.f, -1.f), p);
+  }
+#pragma unroll
+  for (int ofs = 1; ofs < 32; ofs <<= 1) {
+    const float sg = (lane & ofs) ? -1.f : 1.f;     // upper half of the butterfly: other - v, lower: v + other
+    const uint64_t sg2 = pack_f32x2(sg, sg);
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      uint32_t lo, hi;
+      unpack_u32x2(v01[s], lo, hi);
+      const uint64_t o01 = pack_u32x2(__shfl_xor_sync(0xffffffffu, lo, ofs), __shfl_xor_sync(0xffffffffu, hi, ofs));
+      v01[s] = fma_f32x2(v01[s], sg2, o01);
+      unpack_u32x2(v23[s], lo, hi);
+      const uint64_t o23 = pack_u32x2(__shfl_xor_sync(0xffffffffu, lo, ofs), __shfl_xor_sync(0xffffffffu, hi, ofs));
+      v23[s] = fma_f32x2(v23[s], sg2, o23);
+    }
+  }
+  {
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      float b0, b1, b2, b3;
+      unpack_f32x2(v01[s], b0, b1); unpack_f32x2(v23[s], b2, b3);
+      s_x[r][s][t] = make_float4(b0, b1, b2, b3);
+    }
+    named_bar_sync_64(1 + r);
+    const uint64_t sg2 = w ? pack_f32x2(-1.f, -1.f) : pack_f32x2(1.f, 1.f);         // warp 1 (upper half): other - v
+#pragma unroll
+    for (int s = 0; s < K; ++s) {
+      const float4 o = s_x[r][s][t ^ 32];
+      v01[s] = fma_f32x2(v01[s], sg2, pack_f32x2(o.x, o.y));
+      v23[s] = fma_f32x2(v23[s], sg2, pack_f32x2(o.z, o.w));
+    }
+  }
+
+  // ---- per-token abs-max -> delta ----
+  float m = 0.f;
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    float b0, b1, b2, b3;
+    unpack_f32x2(v01[s], b0, b1); unpack_f32x2(v23[s], b2, b3);
+    m = fmaxf(m, fmaxf(fmaxf(fabsf(b0), fabsf(b1)), fmaxf(fabsf(b2), fabsf(b3))));
+  }
+  m = warp_max(m);
+  if (lane == 0) s_m[r][w] = m;
+  named_bar_sync_64(1 + r);
+  m = fmaxf(s_m[r][0], s_m[r][1]);
+  float delta = __fdiv_rn(m, a.n_levels);
+  if (delta < 1.0e-6f) delta = 1.0e-6f;                                  // base_quantizer.py:122-128
+  const float rc = __frcp_rn(delta);
+  const uint64_t r2 = pack_f32x2(rc, rc), nd2 = pack_f32x2(-delta, -delta), magic2 = pack_f32x2(12582912.0f, 12582912.0f);
+
+  // ---- quantize, pack 4 codes per lane and segment, store ----
+  int sum = 0;
+  int8_t* qrow = a.q + row * a.ldq + pos;
+#pragma unroll
+  for (int s = 0; s < K; ++s) {
+    uint32_t c0, c1, c2, c3;
+    unpack_u32x2(div_rn_hoisted_rne2(v01[s], nd2, r2, magic2), c0, c1);
+    unpack_u32x2(div_rn_hoisted_rne2(v23[s], nd2, r2, magic2), c2, c3);
+    const uint32_t packed = __byte_perm(__byte_perm(c0, c1, 0x0040), __byte_perm(c2, c3, 0x0040), 0x5410);
+    sum = __dp4a((int)packed, 0x01010101, sum);
+    stg_stream4(qrow + s * 256, packed);
+    if (a.y_out != nullptr) {
+      float b0, b1, b2, b3;
+      unpack_f32x2(v01[s], b0, b1); unpack_f32x2(v23[s], b2, b3);
+      *reinterpret_cast<float4*>(a.y_out + row * a.ldy + s * 256 + pos) = make_float4(b0, b1, b2, b3);
+    }
+  }
+  if (a.rowsum != nullptr) {
+    sum = warp_sum(sum);
+    if (lane == 0) s_s[r][w] = sum;
+    named_bar_sync_64(1 + r);
+    if (t == 0) a.rowsum[row] = s_s[r][0] + s_s[r][1];
+  }
+  if (t == 0) a.delta[row] = delta;
+}
+
+template <typename T, int K, int MINB>
+static int launch_had_warp2(const HadArgs& a, cudaStream_t st) {
+  had_quant_warp2_kernel<T, K, MINB><<<(unsigned)((a.rows + 1) / 2), 128, 0, st>>>(a);
+  B200Q_CHECK_LAUNCH();
+  return B200Q_OK;
+}
+
 template <typename T, int KM>
 static int launch_had_km(const HadArgs& a0, cudaStream_t st) {
   HadArgs a = a0;
@@ -410,6 +573,8 @@ static int launch_had(const HadArgs& a, cudaStream_t st) {
     if (a.K == 8) return launch_had_warp<T, 8>(a, st);
     if (a.K == 12) return launch_had_warp<T, 12>(a, st);   // 1536 = Wan-1.3B hidden
   }
+  if (g_had_warp && a.log2w == 8 && a.K == 20 && vec_ok)   // 5120 = Wan-14B hidden: two warps per row
+    return g_had_warp == 2 ? launch_had_warp2<T, 20, 3>(a, st) : launch_had_warp2<T, 20, 2>(a, st);
   if (a.K <= 12) return launch_had_km<T, 12>(a, st);
   if (a.K <= 20) return launch_had_km<T, 20>(a, st);
   return launch_had_km<T, HAD_KMAX>(a, st);
@@ -420,7 +585,7 @@ static int launch_had(const HadArgs& a, cudaStream_t st) {
 using namespace b200q;
 
 extern "C" int b200q_had_set_mode(int warp_kernel) {
-  g_had_warp = warp_kernel != 0;
+  g_had_warp = warp_kernel < 0 ? 0 : (warp_kernel > 2 ? 1 : warp_kernel);   // 2: probe variant (3 CTAs per SM, spills)
   return B200Q_OK;
 }
 
