@@ -19,7 +19,13 @@
 // own softmax thread (TMEM lane = row): legal exactly when P.V(j-1) has completed and P.V(j) has not been issued, which
 // the issue order below guarantees (S(j) complete implies P.V(j-1) complete: one in-order tensor pipe).
 //
-// CTA = 256 queries of one head (two 128-row Q tiles), persistent over (head, query-tile-pair) items; 18 warps:
+// Two kernels, chosen per head on the device (b200q_attn_bf16: Cauchy-Schwarz score bound from the row-norm maxima):
+//   attn_bf16_kp_kernel   bounded heads (every head of the RMS-normed Wan workload): max-free softmax, pipelined over KEY
+//                         BLOCKS with three S/P buffers on CTA pairs - described in front of the kernel further down;
+//   attn_bf16_kernel      the two-tile kernel described here: online softmax for unbounded heads (FAST = false), and the
+//                         max-free softmax in the same structure (FAST = true, b200q_attn_bf16_set_variant(0)).
+//
+// Two-tile kernel: CTA = 256 queries of one head (two 128-row Q tiles), persistent over (head, query-tile-pair) items; 18 warps:
 //   warps 0-7 / 8-15  softmax warps of Q tile 0 / 1: TWO threads per query row (TMEM lane), 64 key columns each - the
 //                     per-tile chain S -> softmax -> P.V -> next S is the critical path, so the softmax of a tile is spread
 //                     over 8 warps; the two half-row maxima / sums meet through shared memory and a named barrier
@@ -1172,9 +1178,9 @@ extern "C" int b200q_attn_bf16_splits(int64_t Lq, int64_t Lk, int num_heads) {
   if (Lq <= 0 || Lk <= 0 || num_heads <= 0) return 1;
   // items are walked by clusters of cl CTAs; the key-pipelined kernel (the one Wan's RMS-normed heads take) works on
   // 256-query items in CTA pairs, the two-tile kernel on 256 * cl
-  const bool qres = g_fa_kp && g_fa_fast_poly != -1;
-  const int cl = qres ? 2 : g_fa_cl;
-  const int rows = qres ? 2 * BQ : 2 * BQ * cl;
+  const bool kp = g_fa_kp && g_fa_fast_poly != -1;
+  const int cl = kp ? 2 : g_fa_cl;
+  const int rows = kp ? 2 * BQ : 2 * BQ * cl;
   const long long items = ((Lq + rows - 1) / rows) * num_heads;
   const int nb = (int)((Lk + BKEY - 1) / BKEY), sms = sm_count() / cl;
   int best = 1;
